@@ -1,0 +1,236 @@
+/* stba.h — C ABI of libstba.so, the B200-native bundle-adjustment hot path.
+ *
+ * Plain C: pointers, sizes, POD structs.  No torch / C++ types cross this boundary.
+ * Every function returns an int status (STBA_OK == 0), never throws, and is not
+ * re-entrant on one handle.  All `const T*` array arguments are HOST pointers unless a
+ * name ends in `_dev`.
+ *
+ * What each group replaces in the reference (paths relative to /root/reference):
+ *
+ *   stba_problem_*            the subset of `ceres::Problem` the examples call:
+ *                             AddResidualBlock   st20-g2o/src/include/test_ceres.h:119-121,
+ *                                                st17-ceres/src/include/solver.hpp:267,317,364
+ *                             AddParameterBlock  test_ceres.h:124, solver.hpp:270,321,367-368
+ *                             SetParameterBlockConstant  test_ceres.h:127-130
+ *                             SetParameterLower/UpperBound  st17-ceres/src/ceres_bound.cpp:52-53
+ *   stba_problem_solve        `ceres::Solve(options, &problem, &summary)`  test_ceres.h:148,
+ *                             solver.hpp:286,332,378
+ *   stba_options              `ceres::Solver::Options` fields set at test_ceres.h:133-145,
+ *                             solver.hpp:272-282 (+ the Ceres defaults they rely on)
+ *   stba_summary/_iteration   `ceres::Solver::Summary` (BriefReport, solver.hpp:290) and
+ *                             `ceres::IterationSummary` (test_ceres.h:89, solver.hpp:228,448)
+ *   stba_iteration_callback   `ceres::IterationCallback::operator()`  test_ceres.h:83-96
+ *   STBA_MANIFOLD_*           `LieLocalParameterization<SO3d>` test_ceres.h:14-45 and
+ *                             `LieR3LocalParameterization` solver.hpp:63-94
+ *   stba_ba_*                 the structure-of-arrays engine underneath (what `ceres::Solve`
+ *                             does internally for a reprojection problem; SURVEY.md §8 a4, a9,
+ *                             a10).  Used directly by bench.py and by the per-kernel parity tests.
+ */
+#ifndef STBA_H_
+#define STBA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define STBA_OK 0
+#define STBA_ERR_INVALID_ARGUMENT 1
+#define STBA_ERR_CUDA 2
+#define STBA_ERR_NO_DEVICE 3
+#define STBA_ERR_UNSUPPORTED 4
+#define STBA_ERR_OVERFLOW 5
+#define STBA_ERR_COMM 6
+#define STBA_ERR_SOLVER 7
+
+/* ---- ceres::TerminationType -------------------------------------------------------- */
+#define STBA_CONVERGENCE 0
+#define STBA_NO_CONVERGENCE 1
+#define STBA_FAILURE 2
+#define STBA_USER_SUCCESS 3
+#define STBA_USER_FAILURE 4
+
+/* ---- ceres::CallbackReturnType ----------------------------------------------------- */
+#define STBA_SOLVER_CONTINUE 0
+#define STBA_SOLVER_ABORT 1
+#define STBA_SOLVER_TERMINATE_SUCCESSFULLY 2
+
+/* ---- ceres::LinearSolverType (the two values the reference uses) -------------------- */
+#define STBA_DENSE_QR 0       /* solver.hpp:282,327,374  — small camera system, no Schur */
+#define STBA_SPARSE_SCHUR 1   /* test_ceres.h:145 */
+
+/* ---- manifolds of a parameter block ------------------------------------------------- */
+#define STBA_MANIFOLD_EUCLIDEAN 0
+#define STBA_MANIFOLD_SO3_QUAT_XYZW_RIGHT 1 /* q <- q * exp(d), test_ceres.h:22-29 */
+#define STBA_MANIFOLD_SO3_LOG_RIGHT 2       /* x <- log(exp(x) exp(d)), solver.hpp:67-78 */
+
+/* ---- reduced-system (dense camera Cholesky) back end -------------------------------- */
+#define STBA_DENSE_OWN 0      /* hand-written blocked Cholesky (csrc/stba_chol.cu) */
+#define STBA_DENSE_CUSOLVER 1 /* cusolverDnDpotrf/Dpotrs — the library yard-stick */
+
+typedef struct stba_options {
+  /* Ceres 2.0/2.1 Solver::Options defaults; see stba_options_init */
+  int32_t max_num_iterations;              /* 50 */
+  int32_t max_num_consecutive_invalid_steps; /* 5 */
+  int32_t jacobi_scaling;                  /* 1 */
+  int32_t linear_solver_type;              /* STBA_SPARSE_SCHUR */
+  int32_t update_state_every_iteration;    /* 0; test_ceres.h:138 sets it for the callback */
+  int32_t minimizer_progress_to_stdout;    /* 0; solver.hpp:278 */
+  int32_t num_threads;                     /* accepted and ignored (reference sets 1) */
+  int32_t dense_backend;                   /* STBA_DENSE_OWN */
+  double initial_trust_region_radius;      /* 1e4 */
+  double max_trust_region_radius;          /* 1e16 */
+  double min_trust_region_radius;          /* 1e-32 */
+  double min_relative_decrease;            /* 1e-3 */
+  double min_lm_diagonal;                  /* 1e-6 */
+  double max_lm_diagonal;                  /* 1e32 */
+  double function_tolerance;               /* 1e-6 */
+  double gradient_tolerance;               /* 1e-10 */
+  double parameter_tolerance;              /* 1e-8 */
+} stba_options;
+
+typedef struct stba_iteration {
+  int32_t iteration;
+  int32_t step_is_valid;
+  int32_t step_is_successful;
+  int32_t reserved;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double gradient_norm;
+  double step_norm;
+  double relative_decrease;
+  double trust_region_radius;
+  double iteration_time_ms;      /* device+host wall time of this iteration */
+} stba_iteration;
+
+typedef struct stba_summary {
+  int32_t termination_type;
+  int32_t num_iterations;            /* records written to `iterations` (incl. iteration 0) */
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  double initial_cost;
+  double final_cost;
+  double total_time_ms;              /* LM loop only, set-up excluded */
+  double time_linearize_ms;          /* device time per phase, summed over iterations */
+  double time_schur_ms;
+  double time_dense_ms;
+  double time_backsub_ms;
+  double time_cost_ms;
+  int64_t gpu_launches;              /* kernels launched by the LM loop */
+  char message[192];
+  stba_iteration* iterations;        /* caller-allocated, may be NULL */
+  int32_t iterations_capacity;
+  int32_t reserved;
+} stba_summary;
+
+/* returns STBA_SOLVER_*; called synchronously on the solving thread after every iteration */
+typedef int32_t (*stba_iteration_callback)(const stba_iteration* it, void* user);
+
+void stba_options_init(stba_options* o);
+const char* stba_version(void);
+const char* stba_status_string(int status);
+/* number of CUDA devices visible (0 when none / no driver) */
+int stba_device_count(void);
+/* measured fp64 FMA peak of `device` in TFLOP/s (register-resident DFMA chains, best of reps) —
+ * the denominator of the fp64-pipe roofline; MEASURED_PEAKS.json has no fp64 figure */
+int stba_peak_fp64(int device, int reps, double* tflops);
+
+/* ==================================================================================== */
+/* Engine level: structure-of-arrays bundle adjustment on one device.                   */
+/* Layout: cam_q f64[n_cam,4] xyzw, cam_t f64[n_cam,3], lm f64[n_lm,3],  */
+/* obs_cam i32[n_obs], obs_lm i32[n_obs] (non-decreasing = landmark-major,               */
+/* test_ceres.h:109-110), obs_uv f64[n_obs,2], cam_const u8[n_cam], lm_const u8[n_lm]    */
+/* (NULL = all free; all-constant landmarks = the PnP problem of solver.hpp:247-385).    */
+/* ==================================================================================== */
+typedef struct stba_ba stba_ba;
+
+int stba_ba_create(stba_ba** out, int device, int32_t n_cam, int32_t n_lm, int64_t n_obs,
+                   const double* cam_q, const double* cam_t, const double* lm,
+                   const int32_t* obs_cam, const int32_t* obs_lm, const double* obs_uv,
+                   const uint8_t* cam_const, const uint8_t* lm_const);
+void stba_ba_destroy(stba_ba* ba);
+
+int stba_ba_set_state(stba_ba* ba, const double* cam_q, const double* cam_t, const double* lm);
+int stba_ba_get_state(stba_ba* ba, double* cam_q, double* cam_t, double* lm);
+
+/* device-side snapshot / restore of the state (no host traffic; used to re-run a solve from x0) */
+int stba_ba_save_state(stba_ba* ba);
+int stba_ba_restore_state(stba_ba* ba);
+
+/* Integer preprocessing (bit-exact contract; restates DataManager::Jacobian()/Hessian(),
+ * st20-g2o/src/include/sim_data.h:108-159, in sparse form).  Any output may be NULL. */
+int stba_ba_get_index(stba_ba* ba, int32_t* lm_deg, int32_t* cam_deg, int32_t* lm_ptr,
+                      int32_t* cam_ptr, int32_t* cam_perm);
+/* co-visibility: strictly-lower camera pairs (i>j, both free or not) sharing >= 1 landmark,
+ * as sorted keys i*n_cam+j.  Call with keys==NULL to get the count. */
+int stba_ba_get_covis(stba_ba* ba, int64_t* keys, int64_t* n_keys);
+
+/* One linearisation at the current state: residual + exact Jacobian + J^T J / J^T r block
+ * accumulation (J never stored).  Blocks stay on the device. */
+int stba_ba_linearize(stba_ba* ba);
+/* Hcc f64[n_cam,21] (upper triangle, row-major, tangent order [theta,t]), gc f64[n_cam,6],
+ * Hll f64[n_lm,6] (xx,xy,xz,yy,yz,zz), gl f64[n_lm,3], cost = 1/2 |r|^2.  Any may be NULL. */
+int stba_ba_get_blocks(stba_ba* ba, double* Hcc, double* gc, double* Hll, double* gl, double* cost);
+
+/* Build the damped reduced camera system for trust-region `radius` from the current
+ * linearisation (Jacobi scaling taken from the FIRST linearisation of this handle, as Ceres
+ * does) and copy it out: S f64[n,n] column-major (lower triangle valid), rhs f64[n],
+ * n = 6 * (number of non-constant cameras).  S / rhs may be NULL (then only built). */
+int stba_ba_reduced_system(stba_ba* ba, double radius, const stba_options* opt, double* S,
+                           double* rhs, int32_t* n);
+/* Solve the reduced system built above, back-substitute; returns the (unscaled) LM step
+ * y such that x+ = Plus(x, -y): yc f64[n_cam,6] (zero rows for constant cameras), yl f64[n_lm,3]. */
+int stba_ba_solve_step(stba_ba* ba, int dense_backend, double* yc, double* yl,
+                       double* model_cost_change);
+
+/* Full Ceres-faithful trust-region LM on device-resident state. */
+int stba_ba_solve(stba_ba* ba, const stba_options* opt, stba_summary* summary,
+                  stba_iteration_callback cb, void* user);
+
+/* Timing helpers (CUDA events on the engine's own stream; warm-up is the caller's job).
+ * phase: 0 = linearise (lin_lm + lin_cam), 1 = lin_lm only, 2 = lin_cam only, 3 = schur build,
+ * 4 = dense factor+solve, 5 = back-substitution+update, 6 = candidate cost.
+ * Writes `reps` per-launch durations in milliseconds; flush_l2 != 0 rewrites a >L2 buffer
+ * between repetitions (outside the timed region). */
+int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms);
+/* kernels launched on this handle since creation */
+int64_t stba_ba_launch_count(stba_ba* ba);
+
+/* Multi-GPU: landmark-sharded, one handle per rank holding ALL cameras and its own landmarks /
+ * observations; one ncclAllReduce of [S | rhs | scalars] per linearisation. */
+#define STBA_UNIQUE_ID_BYTES 128
+int stba_comm_unique_id(char* id_out /* STBA_UNIQUE_ID_BYTES */);
+int stba_ba_comm_init(stba_ba* ba, int rank, int nranks, const char* id);
+
+/* ==================================================================================== */
+/* Problem level: the ceres::Problem-shaped front door (pointer identity = block identity) */
+/* ==================================================================================== */
+typedef struct stba_problem stba_problem;
+
+int stba_problem_create(stba_problem** out);
+void stba_problem_destroy(stba_problem* p);
+/* ceres::Problem::AddParameterBlock(values, size, local_parameterization); idempotent */
+int stba_problem_add_parameter_block(stba_problem* p, double* values, int size, int manifold);
+int stba_problem_set_parameter_block_constant(stba_problem* p, double* values);
+int stba_problem_set_parameter_lower_bound(stba_problem* p, double* values, int index, double v);
+int stba_problem_set_parameter_upper_bound(stba_problem* p, double* values, int index, double v);
+/* n x AddResidualBlock(ProjectFactor::Create(uv), nullptr, {so3, pos, landmark})
+ * (test_ceres.h:111-121): so3[i] -> 4 doubles xyzw, pos[i] -> 3, landmark[i] -> 3, uv f64[n,2] */
+int stba_problem_add_reprojection(stba_problem* p, int64_t n, double* const* so3,
+                                  double* const* pos, double* const* landmark, const double* uv);
+/* n x AddResidualBlock(PnP functor(point, feature), nullptr, {so3, pos}) (solver.hpp:260-268);
+ * rot_manifold says how `rot` is stored (quaternion, or so3.log() for the Sized variant :350-361) */
+int stba_problem_add_pnp(stba_problem* p, int64_t n, double* rot, double* pos, int rot_manifold,
+                         const double* points /* n,3 */, const double* uv /* n,2 */);
+int stba_problem_num_residual_blocks(stba_problem* p, int64_t* n);
+int stba_problem_num_parameter_blocks(stba_problem* p, int64_t* n);
+int stba_problem_solve(stba_problem* p, const stba_options* opt, stba_summary* summary,
+                       stba_iteration_callback cb, void* user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STBA_H_ */

@@ -1,0 +1,21 @@
+// Dense reduced-camera solve (own back end).  Interface only in this file; kernels in stba_chol_impl.cuh.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/stba.h"
+
+namespace stba {
+
+struct CholWorkspace {
+  double* buf = nullptr;   // allocated lazily by chol_factor_solve
+  size_t bytes = 0;
+};
+
+// In-place lower Cholesky of the column-major n x n matrix S (leading dimension n) followed by
+// the two triangular solves on rhs (n).  dev_info <- 0 on success, k > 0 if the leading minor k
+// is not positive definite (LAPACK convention).  *n_launches += kernels launched.
+int chol_factor_solve(CholWorkspace& ws, double* S, int n, double* rhs, int* dev_info, cudaStream_t stream,
+                      int* n_launches);
+
+}  // namespace stba

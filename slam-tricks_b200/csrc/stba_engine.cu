@@ -1,0 +1,962 @@
+// libstba.so — engine + C ABI (see include/stba.h).  B200 / sm_100a only; there is no CPU path:
+// every entry point that computes anything fails with STBA_ERR_NO_DEVICE when no GPU is visible.
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <limits>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/stba.h"
+#include "stba_chol.cuh"
+#include "stba_kernels.cuh"
+
+namespace stba {
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      fprintf(stderr, "[stba] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, \
+              __LINE__, cudaGetErrorString(e_));                                              \
+      return STBA_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+#define CKS(call)                                                              \
+  do {                                                                         \
+    cusolverStatus_t s_ = (call);                                              \
+    if (s_ != CUSOLVER_STATUS_SUCCESS) {                                       \
+      fprintf(stderr, "[stba] cuSOLVER error %d at %s:%d\n", (int)s_, __FILE__, __LINE__); \
+      return STBA_ERR_SOLVER;                                                  \
+    }                                                                          \
+  } while (0)
+#define CKN(call)                                                              \
+  do {                                                                         \
+    ncclResult_t r_ = (call);                                                  \
+    if (r_ != ncclSuccess) {                                                   \
+      fprintf(stderr, "[stba] NCCL error %s at %s:%d\n", ncclGetErrorString(r_), __FILE__, __LINE__); \
+      return STBA_ERR_COMM;                                                    \
+    }                                                                          \
+  } while (0)
+#define CKR(call)                 \
+  do {                            \
+    int r_ = (call);              \
+    if (r_ != STBA_OK) return r_; \
+  } while (0)
+
+enum Scalar {
+  SC_COST = 0,   // 1/2 |r|^2 at x (this rank's landmarks)
+  SC_CAND,       // 1/2 |r|^2 at x+
+  SC_MCC_L,      // sum y_l.(g_l + D_l^2 y_l)
+  SC_STEP2_L,    // |P+ - P|^2
+  SC_XN2_L,      // |P+|^2
+  SC_MCC_C,      // sum y_c.(g_c + D_c^2 y_c)
+  SC_STEP2_C,
+  SC_XN2_C,
+  SC_G2,         // gradient 2-norm^2 (ambient projected form)
+  SC_GMAX,       // gradient max-norm
+  SC_XNORM2,     // |x|^2
+  SC_COUNT = 16
+};
+
+enum Phase { PH_LIN = 0, PH_SCHUR, PH_DENSE, PH_BACKSUB, PH_COST, PH_COUNT };
+
+struct Engine {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int n_cam = 0, n_lm = 0, n_free = 0, n = 0;  // n = 6 * n_free
+  int64_t n_obs = 0, n_blk = 0, n_inc = 0;
+  int n_chunk = 0, chunk_size = 0, sm_count = 148, max_grid = 148 * 16;
+  int64_t launches = 0;
+  bool has_lm_const = false;
+
+  double *cam_q = nullptr, *cam_t = nullptr, *lm4 = nullptr;
+  double *cam_q2 = nullptr, *cam_t2 = nullptr, *lm4_2 = nullptr;
+  double *Rt = nullptr, *Rt2 = nullptr;
+  double *save_q = nullptr, *save_t = nullptr, *save_lm4 = nullptr;   // device-side snapshot (stba_ba_save_state)
+  int *obs_cam = nullptr, *obs_lm = nullptr, *lm_ptr = nullptr, *lm_deg = nullptr;
+  double* obs_uv = nullptr;
+  int *cam_ptr = nullptr, *cam_deg = nullptr, *cam_perm = nullptr, *cobs_lm = nullptr;
+  double* cobs_uv = nullptr;
+  uint8_t *cam_const = nullptr, *lm_const = nullptr;
+  int* free_of = nullptr;
+  int *chunk_cam = nullptr, *chunk_beg = nullptr, *chunk_end = nullptr, *cam_chunk_ptr = nullptr;
+  int64_t* blk_ptr = nullptr;
+  uint64_t* inc = nullptr;
+  int* dup_flag = nullptr;
+  double *Hcc = nullptr, *gc = nullptr, *Hll = nullptr, *gl = nullptr, *sc = nullptr, *sl = nullptr;
+  bool have_scale = false, linearized = false, reduced_built = false;
+  double *Dc2 = nullptr, *Dl2 = nullptr, *Linv = nullptr, *hl = nullptr, *E = nullptr;
+  double *S = nullptr, *rhs = nullptr, *yc = nullptr, *yl = nullptr, *chunk_acc = nullptr;
+  double* partial = nullptr;
+  unsigned int* counter = nullptr;
+  double *scal = nullptr, *scal_host = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  double* potrf_work = nullptr;
+  int potrf_lwork = 0;
+  int *dev_info = nullptr, *info_host = nullptr;
+  CholWorkspace chol;
+  double* flush_buf = nullptr;
+  size_t flush_n = 0;
+  cudaEvent_t ev[PH_COUNT + 1] = {};
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  std::vector<void*> allocs;
+
+  template <typename T>
+  int alloc(T** p, size_t count) {
+    *p = nullptr;
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return STBA_OK;
+  }
+  int grid_for(int64_t items, int per_block) const {
+    const int64_t g = (items + per_block - 1) / per_block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, max_grid));
+  }
+  ~Engine() {
+    if (stream) cudaStreamSynchronize(stream);
+    for (void* p : allocs) cudaFree(p);
+    if (scal_host) cudaFreeHost(scal_host);
+    if (info_host) cudaFreeHost(info_host);
+    if (cusolver) cusolverDnDestroy(cusolver);
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    if (comm) ncclCommDestroy(comm);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  int setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double* h_q, const double* h_t,
+            const double* h_lm, const int32_t* h_oc, const int32_t* h_ol, const double* h_uv,
+            const uint8_t* h_cc, const uint8_t* h_lc);
+  int build_pairs();
+  int set_state(const double* h_q, const double* h_t, const double* h_lm);
+  int get_state(double* h_q, double* h_t, double* h_lm);
+  int linearize();
+  int post_linearize(const stba_options& opt, bool want_grad);
+  int build_reduced(double radius, const stba_options& opt);
+  int dense_solve(int backend);
+  int step_from_solution();
+  int candidate_cost();
+  int fetch_scalars();
+  int allreduce_sum(double* p, size_t count);
+  int allreduce_max(double* p, size_t count);
+  int solve(const stba_options& opt, stba_summary* sum, stba_iteration_callback cb, void* user);
+};
+
+#define LAUNCH(e, kernel, grid, block, ...)                   \
+  do {                                                        \
+    kernel<<<(grid), (block), 0, (e)->stream>>>(__VA_ARGS__); \
+    ++(e)->launches;                                          \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+int Engine::allreduce_sum(double* p, size_t count) {
+  if (nranks <= 1 || count == 0) return STBA_OK;
+  CKN(ncclAllReduce(p, p, count, ncclDouble, ncclSum, comm, stream));
+  return STBA_OK;
+}
+int Engine::allreduce_max(double* p, size_t count) {
+  if (nranks <= 1 || count == 0) return STBA_OK;
+  CKN(ncclAllReduce(p, p, count, ncclDouble, ncclMax, comm, stream));
+  return STBA_OK;
+}
+
+int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double* h_q, const double* h_t,
+                  const double* h_lm, const int32_t* h_oc, const int32_t* h_ol, const double* h_uv,
+                  const uint8_t* h_cc, const uint8_t* h_lc) {
+  if (ncam < 0 || nlm < 0 || nobs < 0 || nobs > (int64_t)std::numeric_limits<int32_t>::max() - 1024)
+    return STBA_ERR_INVALID_ARGUMENT;
+  if ((ncam && (!h_q || !h_t)) || (nlm && !h_lm) || (nobs && (!h_oc || !h_ol || !h_uv)))
+    return STBA_ERR_INVALID_ARGUMENT;
+  // host-side validation of the ordering contract (test_ceres.h:109-110: landmark-major)
+  for (int64_t i = 0; i < nobs; ++i) {
+    if (h_oc[i] < 0 || h_oc[i] >= ncam || h_ol[i] < 0 || h_ol[i] >= nlm) return STBA_ERR_INVALID_ARGUMENT;
+    if (i && h_ol[i] < h_ol[i - 1]) return STBA_ERR_INVALID_ARGUMENT;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STBA_ERR_NO_DEVICE; }
+  if (dev < 0 || dev >= ndev) return STBA_ERR_INVALID_ARGUMENT;
+  device = dev;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  sm_count = prop.multiProcessorCount;
+  max_grid = sm_count * 16;
+  CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  n_cam = ncam; n_lm = nlm; n_obs = nobs;
+
+  // ---- free-camera map (host) ----
+  std::vector<int> h_free(std::max(ncam, 1), -1);
+  std::vector<uint8_t> h_const(std::max(ncam, 1), 0);
+  n_free = 0;
+  for (int c = 0; c < ncam; ++c) {
+    h_const[c] = h_cc ? (h_cc[c] != 0) : 0;
+    h_free[c] = h_const[c] ? -1 : n_free++;
+  }
+  n = 6 * n_free;
+  has_lm_const = false;
+  if (h_lc) for (int l = 0; l < nlm; ++l) if (h_lc[l]) { has_lm_const = true; break; }
+
+  // ---- device arrays ----
+  CKR(alloc(&cam_q, 4 * (size_t)ncam)); CKR(alloc(&cam_t, 3 * (size_t)ncam)); CKR(alloc(&lm4, 4 * (size_t)nlm));
+  CKR(alloc(&cam_q2, 4 * (size_t)ncam)); CKR(alloc(&cam_t2, 3 * (size_t)ncam)); CKR(alloc(&lm4_2, 4 * (size_t)nlm));
+  CKR(alloc(&Rt, kCamTile * (size_t)ncam)); CKR(alloc(&Rt2, kCamTile * (size_t)ncam));
+  CKR(alloc(&obs_cam, (size_t)nobs)); CKR(alloc(&obs_lm, (size_t)nobs)); CKR(alloc(&obs_uv, 2 * (size_t)nobs));
+  CKR(alloc(&lm_ptr, (size_t)nlm + 1)); CKR(alloc(&lm_deg, (size_t)nlm));
+  CKR(alloc(&cam_ptr, (size_t)ncam + 1)); CKR(alloc(&cam_deg, (size_t)ncam));
+  CKR(alloc(&cam_perm, (size_t)nobs)); CKR(alloc(&cobs_lm, (size_t)nobs)); CKR(alloc(&cobs_uv, 2 * (size_t)nobs));
+  CKR(alloc(&cam_const, (size_t)ncam)); CKR(alloc(&free_of, (size_t)ncam));
+  if (has_lm_const) CKR(alloc(&lm_const, (size_t)nlm));
+  CKR(alloc(&Hcc, 21 * (size_t)ncam)); CKR(alloc(&gc, 6 * (size_t)ncam));
+  CKR(alloc(&Hll, 6 * (size_t)nlm)); CKR(alloc(&gl, 3 * (size_t)nlm));
+  CKR(alloc(&sc, 6 * (size_t)ncam)); CKR(alloc(&sl, 3 * (size_t)nlm));
+  CKR(alloc(&Dc2, 6 * (size_t)ncam)); CKR(alloc(&Dl2, 3 * (size_t)nlm));
+  CKR(alloc(&Linv, 6 * (size_t)nlm)); CKR(alloc(&hl, 3 * (size_t)nlm));
+  CKR(alloc(&yc, 6 * (size_t)ncam)); CKR(alloc(&yl, 3 * (size_t)nlm));
+  CKR(alloc(&partial, (size_t)max_grid * 8)); CKR(alloc(&counter, 1)); CKR(alloc(&scal, SC_COUNT));
+  CKR(alloc(&dev_info, 1)); CKR(alloc(&dup_flag, 1));
+  CK(cudaMallocHost(&scal_host, SC_COUNT * sizeof(double)));
+  CK(cudaMallocHost(&info_host, sizeof(int)));
+  CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+  CK(cudaMemsetAsync(scal, 0, SC_COUNT * sizeof(double), stream));
+  CK(cudaMemsetAsync(dup_flag, 0, sizeof(int), stream));
+  CK(cudaMemsetAsync(yc, 0, 6 * (size_t)std::max(ncam, 1) * sizeof(double), stream));
+
+  CK(cudaMemcpyAsync(obs_cam, h_oc, nobs * sizeof(int), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(obs_lm, h_ol, nobs * sizeof(int), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(obs_uv, h_uv, 2 * nobs * sizeof(double), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(cam_const, h_const.data(), ncam, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(free_of, h_free.data(), ncam * sizeof(int), cudaMemcpyHostToDevice, stream));
+  if (has_lm_const) CK(cudaMemcpyAsync(lm_const, h_lc, nlm, cudaMemcpyHostToDevice, stream));
+  CKR(set_state(h_q, h_t, h_lm));
+
+  // ---- integer preprocessing on the device (bit-exact contract) ----
+  CK(cudaMemsetAsync(lm_deg, 0, std::max(nlm, 1) * sizeof(int), stream));
+  CK(cudaMemsetAsync(cam_deg, 0, std::max(ncam, 1) * sizeof(int), stream));
+  if (nobs) {
+    LAUNCH(this, k_histogram, grid_for(nobs, 256), 256, nobs, obs_lm, lm_deg);
+    LAUNCH(this, k_histogram, grid_for(nobs, 256), 256, nobs, obs_cam, cam_deg);
+  }
+  LAUNCH(this, (k_exclusive_scan<int, int>), 1, 1024, (int64_t)nlm, lm_deg, lm_ptr);
+  LAUNCH(this, (k_exclusive_scan<int, int>), 1, 1024, (int64_t)ncam, cam_deg, cam_ptr);
+  if (nobs) {
+    int* cursor = nullptr;
+    CKR(alloc(&cursor, (size_t)ncam));
+    CK(cudaMemsetAsync(cursor, 0, ncam * sizeof(int), stream));
+    LAUNCH(this, k_bucket_scatter, grid_for(nobs, 256), 256, nobs, obs_cam, cam_ptr, cursor, cam_perm);
+    LAUNCH(this, k_sort_buckets_i32, std::min(ncam, max_grid), 256, ncam, cam_ptr, cam_perm);
+    LAUNCH(this, k_gather_cam_major, grid_for(nobs, 256), 256, nobs, cam_perm, obs_lm, obs_uv, cobs_lm, cobs_uv);
+  }
+
+  // ---- chunk table of the camera-major passes (host logic from cam_ptr) ----
+  std::vector<int> h_cam_ptr((size_t)ncam + 1, 0);
+  CK(cudaMemcpyAsync(h_cam_ptr.data(), cam_ptr, ((size_t)ncam + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  {
+    // aim for >= 16 warps per SM, chunks between 64 and 2048 observations (multiple of 32)
+    int64_t target = nobs / ((int64_t)sm_count * 16) + 1;
+    chunk_size = (int)std::min<int64_t>(2048, std::max<int64_t>(64, (target + 31) / 32 * 32));
+    std::vector<int> cc, cb, ce, ccp((size_t)ncam + 1, 0);
+    for (int c = 0; c < ncam; ++c) {
+      ccp[c] = (int)cc.size();
+      if (h_const[c]) continue;
+      for (int b = h_cam_ptr[c]; b < h_cam_ptr[c + 1]; b += chunk_size) {
+        cc.push_back(c); cb.push_back(b); ce.push_back(std::min(b + chunk_size, h_cam_ptr[c + 1]));
+      }
+    }
+    ccp[ncam] = (int)cc.size();
+    n_chunk = (int)cc.size();
+    CKR(alloc(&chunk_cam, (size_t)n_chunk)); CKR(alloc(&chunk_beg, (size_t)n_chunk)); CKR(alloc(&chunk_end, (size_t)n_chunk));
+    CKR(alloc(&cam_chunk_ptr, (size_t)ncam + 1));
+    CKR(alloc(&chunk_acc, (size_t)n_chunk * kDiagAcc));
+    CK(cudaMemcpyAsync(chunk_cam, cc.data(), n_chunk * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(chunk_beg, cb.data(), n_chunk * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(chunk_end, ce.data(), n_chunk * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(cam_chunk_ptr, ccp.data(), ((size_t)ncam + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  CKR(build_pairs());
+
+  // ---- Schur / dense workspaces ----
+  CKR(alloc(&E, 18 * (size_t)nobs));
+  CKR(alloc(&S, (size_t)n * n)); CKR(alloc(&rhs, (size_t)n));
+  CK(cudaMemsetAsync(S, 0, std::max<size_t>((size_t)n * n, 1) * sizeof(double), stream));
+  if (cusolverDnCreate(&cusolver) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
+  CKS(cusolverDnSetStream(cusolver, stream));
+  if (n > 0) {
+    CKS(cusolverDnDpotrf_bufferSize(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, n, &potrf_lwork));
+    CKR(alloc(&potrf_work, (size_t)potrf_lwork));
+  }
+  CK(cudaStreamSynchronize(stream));
+  return STBA_OK;
+}
+
+int Engine::build_pairs() {
+  n_blk = (int64_t)n_free * (n_free - 1) / 2;
+  if (n_blk > (int64_t)1 << 31) return STBA_ERR_OVERFLOW;
+  int* cnt = nullptr;
+  CKR(alloc(&cnt, (size_t)n_blk));
+  CKR(alloc(&blk_ptr, (size_t)n_blk + 1));
+  CK(cudaMemsetAsync(cnt, 0, std::max<int64_t>(n_blk, 1) * sizeof(int), stream));
+  const uint8_t* lc = has_lm_const ? lm_const : nullptr;
+  if (n_lm && n_blk) LAUNCH(this, (k_pair_pass<0>), grid_for(n_lm, 128), 128, n_lm, lm_ptr, obs_cam, free_of, lc, cnt, nullptr, nullptr, dup_flag);
+  LAUNCH(this, (k_exclusive_scan<int, int64_t>), 1, 1024, n_blk, cnt, blk_ptr);
+  CK(cudaMemcpyAsync(&n_inc, blk_ptr + n_blk, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  CKR(alloc(&inc, (size_t)n_inc));
+  if (n_inc) {
+    CK(cudaMemsetAsync(cnt, 0, n_blk * sizeof(int), stream));
+    LAUNCH(this, (k_pair_pass<1>), grid_for(n_lm, 128), 128, n_lm, lm_ptr, obs_cam, free_of, lc, cnt, blk_ptr, inc, dup_flag);
+    LAUNCH(this, k_sort_segments_u64, grid_for(n_blk, kBlock / 32), kBlock, n_blk, blk_ptr, inc);
+  }
+  CK(cudaStreamSynchronize(stream));
+  return STBA_OK;
+}
+
+int Engine::set_state(const double* h_q, const double* h_t, const double* h_lm) {
+  CK(cudaSetDevice(device));
+  if (n_cam) {
+    CK(cudaMemcpyAsync(cam_q, h_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(cam_t, h_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyHostToDevice, stream));
+  }
+  if (n_lm) {
+    // stage the packed [n,3] array in lm4_2 and pad on the device
+    CK(cudaMemcpyAsync(lm4_2, h_lm, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyHostToDevice, stream));
+    LAUNCH(this, k_pad_lm, (n_lm + 255) / 256, 256, n_lm, lm4_2, lm4);
+  }
+  CK(cudaStreamSynchronize(stream));
+  linearized = false;
+  reduced_built = false;
+  return STBA_OK;
+}
+
+int Engine::get_state(double* h_q, double* h_t, double* h_lm) {
+  CK(cudaSetDevice(device));
+  if (n_cam && h_q) CK(cudaMemcpyAsync(h_q, cam_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (n_cam && h_t) CK(cudaMemcpyAsync(h_t, cam_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (n_lm && h_lm) {
+    LAUNCH(this, k_unpad_lm, (n_lm + 255) / 256, 256, n_lm, lm4, lm4_2);
+    CK(cudaMemcpyAsync(h_lm, lm4_2, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  }
+  CK(cudaStreamSynchronize(stream));
+  return STBA_OK;
+}
+
+// residual + Jacobian + J^T J / J^T r blocks at the current x
+int Engine::linearize() {
+  if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q, cam_t, Rt);
+  LAUNCH(this, (k_lin_lm<false>), grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, obs_uv, Rt, lm4, Hll, gl,
+         partial, counter, scal + SC_COST);
+  if (n_chunk)
+    LAUNCH(this, k_lin_cam, grid_for(n_chunk, kBlock / 32), kBlock, n_chunk, chunk_cam, chunk_beg, chunk_end,
+           cobs_lm, cobs_uv, Rt, lm4, chunk_acc);
+  if (n_cam)
+    LAUNCH(this, k_lin_cam_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, cam_const, chunk_acc, Rt, Hcc, gc);
+  CK(cudaGetLastError());
+  linearized = true;
+  reduced_built = false;
+  return STBA_OK;
+}
+
+// multi-GPU reduction of the camera blocks, Jacobi scales on first use, gradient norms
+int Engine::post_linearize(const stba_options& opt, bool want_grad) {
+  if (nranks > 1) {
+    // Hcc and gc are contiguous? no — two collectives in one group
+    CKN(ncclGroupStart());
+    CKN(ncclAllReduce(Hcc, Hcc, 21 * (size_t)n_cam, ncclDouble, ncclSum, comm, stream));
+    CKN(ncclAllReduce(gc, gc, 6 * (size_t)n_cam, ncclDouble, ncclSum, comm, stream));
+    CKN(ncclAllReduce(scal + SC_COST, scal + SC_COST, 1, ncclDouble, ncclSum, comm, stream));
+    CKN(ncclGroupEnd());
+  }
+  if (!have_scale) {
+    const int m = std::max(n_cam, n_lm);
+    if (m) LAUNCH(this, k_jacobi_scale, (m + 127) / 128, 128, n_cam, n_lm, opt.jacobi_scaling, Hcc, Hll, sc, sl);
+    have_scale = true;
+  }
+  if (want_grad) {
+    const uint8_t* lc = has_lm_const ? lm_const : nullptr;
+    // cameras are replicated: only rank 0 counts them before the sum
+    LAUNCH(this, k_grad_norm, grid_for(n_cam + n_lm, kBlock), kBlock, rank == 0 ? n_cam : 0, n_lm, cam_const, lc,
+           cam_q, gc, gl, partial, counter, scal + SC_G2);
+    if (nranks > 1) {
+      // k_grad_norm with n_cam = 0 indexes landmarks from 0: handled by passing n_cam = 0 above
+      CKR(allreduce_sum(scal + SC_G2, 1));
+      CKR(allreduce_max(scal + SC_GMAX, 1));
+    }
+  }
+  CK(cudaGetLastError());
+  return STBA_OK;
+}
+
+// S = H_cc + D_c^2 - sum E E^T (lower triangle, dense column-major), rhs = g_c - sum E h
+int Engine::build_reduced(double radius, const stba_options& opt) {
+  if (!linearized) return STBA_ERR_INVALID_ARGUMENT;
+  const double inv_r = 1.0 / radius;
+  const uint8_t* lc = has_lm_const ? lm_const : nullptr;
+  if (n_cam) LAUNCH(this, k_cam_diag, (6 * n_cam + 127) / 128, 128, n_cam, Hcc, sc, opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dc2);
+  LAUNCH(this, k_schur_lm, grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, obs_uv, Rt, lm4, cam_const, lc, Hll, gl, sl,
+         opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dl2, Linv, hl, E);
+  if (n_free) {
+    if (n_chunk)
+      LAUNCH(this, k_schur_diag, grid_for(n_chunk, kBlock / 32), kBlock, n_chunk, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
+    LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, S, n, rhs,
+           nranks > 1 ? 0 : 1);
+    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, S, n);
+    if (nranks > 1) {
+      CKN(ncclGroupStart());
+      CKN(ncclAllReduce(S, S, (size_t)n * n, ncclDouble, ncclSum, comm, stream));
+      CKN(ncclAllReduce(rhs, rhs, (size_t)n, ncclDouble, ncclSum, comm, stream));
+      CKN(ncclGroupEnd());
+      LAUNCH(this, k_add_cam_blocks, (n_cam + 127) / 128, 128, n_cam, free_of, Hcc, gc, Dc2, S, n, rhs);
+    }
+  }
+  CK(cudaGetLastError());
+  reduced_built = true;
+  return STBA_OK;
+}
+
+// Cholesky of S (in place) and solve; the solution lands in rhs, then yc
+int Engine::dense_solve(int backend) {
+  if (!reduced_built) return STBA_ERR_INVALID_ARGUMENT;
+  CK(cudaMemsetAsync(dev_info, 0, sizeof(int), stream));
+  if (n > 0) {
+    if (backend == STBA_DENSE_CUSOLVER) {
+      CKS(cusolverDnDpotrf(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, n, potrf_work, potrf_lwork, dev_info));
+      CKS(cusolverDnDpotrs(cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, S, n, rhs, n, dev_info));
+      launches += 2;
+    } else {
+      int nl = 0;
+      CKR(chol_factor_solve(chol, S, n, rhs, dev_info, stream, &nl));
+      launches += nl;
+    }
+  }
+  if (n_cam) LAUNCH(this, k_scatter_yc, (6 * n_cam + 127) / 128, 128, n_cam, free_of, rhs, yc);
+  reduced_built = false;  // S now holds the factor
+  CK(cudaGetLastError());
+  return STBA_OK;
+}
+
+// back-substitution, candidate point x+ = Plus(x, -y), step scalars
+int Engine::step_from_solution() {
+  LAUNCH(this, k_backsub, grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, E, yc, Linv, hl, gl, Dl2, lm4, yl, lm4_2,
+         partial, counter, scal + SC_MCC_L);
+  LAUNCH(this, k_cam_update, grid_for(n_cam, kBlock), kBlock, n_cam, cam_const, cam_q, cam_t, yc, gc, Dc2, cam_q2, cam_t2,
+         partial, counter, scal + SC_MCC_C);
+  CK(cudaGetLastError());
+  return STBA_OK;
+}
+
+int Engine::candidate_cost() {
+  if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q2, cam_t2, Rt2);
+  LAUNCH(this, (k_lin_lm<true>), grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, obs_uv, Rt2, lm4_2, nullptr, nullptr,
+         partial, counter, scal + SC_CAND);
+  // landmark-side scalars are per-rank partial sums: SC_CAND, SC_MCC_L, SC_STEP2_L, SC_XN2_L are contiguous
+  CKR(allreduce_sum(scal + SC_CAND, 4));
+  CK(cudaGetLastError());
+  return STBA_OK;
+}
+
+int Engine::fetch_scalars() {
+  CK(cudaMemcpyAsync(scal_host, scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(info_host, dev_info, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  return STBA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Trust-region Levenberg-Marquardt, control flow of Ceres 2.0/2.1 trust_region_minimizer.cc with
+// LevenbergMarquardtStrategy and default options.  The host sees one
+// 128-byte scalar block per iteration; all state stays in HBM.
+// ------------------------------------------------------------------------------------------
+int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_callback cb, void* user) {
+  CK(cudaSetDevice(device));
+  using clk = std::chrono::steady_clock;
+  const auto t_begin = clk::now();
+  const int64_t launches0 = launches;
+  double phase_ms[PH_COUNT] = {0, 0, 0, 0, 0};
+  int n_rec = 0, n_succ = 0, n_unsucc = 0;
+  double min_cost = std::numeric_limits<double>::infinity();
+  int term = STBA_NO_CONVERGENCE;
+  std::string msg;
+  have_scale = false;  // Jacobi scaling is computed at the x0 of THIS solve
+
+  auto add_phase = [&](int ph, cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) phase_ms[ph] += ms;
+  };
+
+  // ---- IterationZero ----
+  CK(cudaEventRecord(ev[0], stream));
+  CKR(linearize());
+  CKR(post_linearize(opt, true));
+  {
+    const uint8_t* lc = has_lm_const ? lm_const : nullptr;
+    LAUNCH(this, k_x_norm, grid_for(n_cam + n_lm, kBlock), kBlock, rank == 0 ? n_cam : 0, n_lm, cam_const, lc, cam_q, cam_t, lm4,
+           partial, counter, scal + SC_XNORM2);
+    CKR(allreduce_sum(scal + SC_XNORM2, 1));
+  }
+  CK(cudaEventRecord(ev[1], stream));
+  CKR(fetch_scalars());
+  add_phase(PH_LIN, ev[0], ev[1]);
+  double x_cost = scal_host[SC_COST];
+  double x_norm = std::sqrt(scal_host[SC_XNORM2]);
+  double radius = opt.initial_trust_region_radius;
+  double decrease_factor = 2.0;
+  int num_invalid = 0;
+  auto t_iter = clk::now();
+
+  stba_iteration it;
+  memset(&it, 0, sizeof(it));
+  it.iteration = 0; it.cost = x_cost; it.gradient_norm = std::sqrt(scal_host[SC_G2]); it.gradient_max_norm = scal_host[SC_GMAX];
+  it.trust_region_radius = radius; it.step_is_valid = 1; it.step_is_successful = 1;
+  const double initial_cost = x_cost;
+  if (!std::isfinite(x_cost)) {
+    term = STBA_FAILURE; msg = "Initial residual evaluation is not finite.";
+  }
+
+  while (term != STBA_FAILURE || n_rec == 0) {
+    // ---- FinalizeIterationAndCheckIfMinimizerCanContinue ----
+    if (it.step_is_successful) ++n_succ; else ++n_unsucc;
+    it.trust_region_radius = radius;
+    it.iteration_time_ms = std::chrono::duration<double, std::milli>(clk::now() - t_iter).count();
+    t_iter = clk::now();
+    if (sum && sum->iterations && n_rec < sum->iterations_capacity) sum->iterations[n_rec] = it;
+    ++n_rec;
+    min_cost = std::min(min_cost, it.cost);
+    if (opt.minimizer_progress_to_stdout)
+      printf("%4d  cost %.6e  d_cost %.3e  |g|max %.3e  |step| %.3e  rho %.3e  radius %.3e  %s\n", it.iteration, it.cost,
+             it.cost_change, it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius,
+             it.step_is_successful ? "ok" : "rejected");
+    if (term == STBA_FAILURE) break;
+    if (cb) {
+      const int r = cb(&it, user);
+      if (r == STBA_SOLVER_ABORT) { term = STBA_USER_FAILURE; msg = "User callback returned SOLVER_ABORT."; break; }
+      if (r == STBA_SOLVER_TERMINATE_SUCCESSFULLY) { term = STBA_USER_SUCCESS; msg = "User callback returned SOLVER_TERMINATE_SUCCESSFULLY."; break; }
+    }
+    if (it.iteration >= opt.max_num_iterations) { term = STBA_NO_CONVERGENCE; msg = "Maximum number of iterations reached."; break; }
+    if (it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) { term = STBA_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
+    if (radius < opt.min_trust_region_radius) { term = STBA_CONVERGENCE; msg = "Minimum trust region radius reached."; break; }
+
+    stba_iteration prev = it;
+    memset(&it, 0, sizeof(it));
+    it.iteration = prev.iteration + 1; it.cost = x_cost;
+    it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
+    it.trust_region_radius = radius;
+
+    // ---- ComputeTrustRegionStep ----
+    CK(cudaEventRecord(ev[0], stream));
+    CKR(build_reduced(radius, opt));
+    CK(cudaEventRecord(ev[1], stream));
+    CKR(dense_solve(opt.dense_backend));
+    CK(cudaEventRecord(ev[2], stream));
+    CKR(step_from_solution());
+    CK(cudaEventRecord(ev[3], stream));
+    CKR(candidate_cost());
+    CK(cudaEventRecord(ev[4], stream));
+    CKR(fetch_scalars());
+    add_phase(PH_SCHUR, ev[0], ev[1]); add_phase(PH_DENSE, ev[1], ev[2]);
+    add_phase(PH_BACKSUB, ev[2], ev[3]); add_phase(PH_COST, ev[3], ev[4]);
+
+    const double mcc = 0.5 * (scal_host[SC_MCC_C] + scal_host[SC_MCC_L]);   // model cost change
+    const double cand_cost = scal_host[SC_CAND];
+    bool valid = (*info_host == 0) && std::isfinite(mcc) && mcc > 0.0;
+    if (!valid) {
+      // ---- HandleInvalidStep ----
+      if (++num_invalid >= opt.max_num_consecutive_invalid_steps) {
+        term = STBA_FAILURE;
+        msg = "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps";
+        it.cost = x_cost;
+        continue;   // records the failed iteration, then leaves
+      }
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      it.cost = x_cost;
+      continue;
+    }
+    num_invalid = 0;
+    it.step_is_valid = 1;
+    const bool cand_ok = std::isfinite(cand_cost);
+    const double step_norm = std::sqrt(scal_host[SC_STEP2_C] + scal_host[SC_STEP2_L]);
+    it.step_norm = step_norm;
+    // ---- ParameterToleranceReached ----
+    if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+      term = STBA_CONVERGENCE; msg = "Parameter tolerance reached."; break;
+    }
+    // ---- FunctionToleranceReached ----
+    if (cand_ok) {
+      it.cost_change = x_cost - cand_cost;
+      if (std::fabs(it.cost_change) <= opt.function_tolerance * x_cost) {
+        term = STBA_CONVERGENCE; msg = "Function tolerance reached."; break;
+      }
+    }
+    const double rho = cand_ok ? (x_cost - cand_cost) / mcc : -std::numeric_limits<double>::max();
+    it.relative_decrease = rho;
+    if (rho > opt.min_relative_decrease) {
+      // ---- accept: x <- x+, re-linearise ----
+      std::swap(cam_q, cam_q2); std::swap(cam_t, cam_t2); std::swap(lm4, lm4_2); std::swap(Rt, Rt2);
+      x_norm = std::sqrt(scal_host[SC_XN2_C] + scal_host[SC_XN2_L]);
+      CK(cudaEventRecord(ev[0], stream));
+      CKR(linearize());
+      CKR(post_linearize(opt, true));
+      CK(cudaEventRecord(ev[1], stream));
+      CKR(fetch_scalars());
+      add_phase(PH_LIN, ev[0], ev[1]);
+      x_cost = scal_host[SC_COST];
+      it.cost = x_cost; it.gradient_norm = std::sqrt(scal_host[SC_G2]); it.gradient_max_norm = scal_host[SC_GMAX];
+      it.step_is_successful = 1;
+      radius = std::min(opt.max_trust_region_radius, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+      decrease_factor = 2.0;
+    } else {
+      it.cost = cand_ok ? cand_cost : x_cost;
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+    }
+  }
+
+  if (sum) {
+    sum->termination_type = term;
+    sum->num_iterations = std::min(n_rec, sum->iterations ? sum->iterations_capacity : n_rec);
+    sum->num_successful_steps = n_succ;
+    sum->num_unsuccessful_steps = n_unsucc;
+    sum->initial_cost = initial_cost;
+    sum->final_cost = x_cost;
+    sum->total_time_ms = std::chrono::duration<double, std::milli>(clk::now() - t_begin).count();
+    sum->time_linearize_ms = phase_ms[PH_LIN]; sum->time_schur_ms = phase_ms[PH_SCHUR]; sum->time_dense_ms = phase_ms[PH_DENSE];
+    sum->time_backsub_ms = phase_ms[PH_BACKSUB]; sum->time_cost_ms = phase_ms[PH_COST];
+    sum->gpu_launches = launches - launches0;
+    snprintf(sum->message, sizeof(sum->message), "%s", msg.c_str());
+    sum->reserved = n_rec;   // total iterations run, even if the record buffer was shorter
+  }
+  return STBA_OK;
+}
+
+}  // namespace stba
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using stba::Engine;
+struct stba_ba { Engine e; };
+
+extern "C" {
+
+void stba_options_init(stba_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 50;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->linear_solver_type = STBA_SPARSE_SCHUR;
+  o->update_state_every_iteration = 0;
+  o->minimizer_progress_to_stdout = 0;
+  o->num_threads = 1;
+  o->dense_backend = STBA_DENSE_CUSOLVER;  // until the own blocked Cholesky is validated on hardware
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+}
+
+const char* stba_version(void) { return "stba 0.1 (sm_100a)"; }
+
+const char* stba_status_string(int s) {
+  switch (s) {
+    case STBA_OK: return "ok";
+    case STBA_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case STBA_ERR_CUDA: return "CUDA error";
+    case STBA_ERR_NO_DEVICE: return "no CUDA device visible (libstba has no CPU path)";
+    case STBA_ERR_UNSUPPORTED: return "unsupported problem structure";
+    case STBA_ERR_OVERFLOW: return "problem too large for 32-bit block indices";
+    case STBA_ERR_COMM: return "NCCL error";
+    case STBA_ERR_SOLVER: return "dense solver error";
+  }
+  return "unknown status";
+}
+
+int stba_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int stba_ba_create(stba_ba** out, int device, int32_t n_cam, int32_t n_lm, int64_t n_obs, const double* cam_q,
+                   const double* cam_t, const double* lm, const int32_t* obs_cam, const int32_t* obs_lm,
+                   const double* obs_uv, const uint8_t* cam_const, const uint8_t* lm_const) {
+  if (!out) return STBA_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  stba_ba* h = new (std::nothrow) stba_ba();
+  if (!h) return STBA_ERR_CUDA;
+  const int r = h->e.setup(device, n_cam, n_lm, n_obs, cam_q, cam_t, lm, obs_cam, obs_lm, obs_uv, cam_const, lm_const);
+  if (r != STBA_OK) { delete h; return r; }
+  int dup = 0;
+  cudaMemcpy(&dup, h->e.dup_flag, sizeof(int), cudaMemcpyDeviceToHost);
+  if (dup) { delete h; return STBA_ERR_UNSUPPORTED; }
+  *out = h;
+  return STBA_OK;
+}
+
+void stba_ba_destroy(stba_ba* ba) {
+  if (!ba) return;
+  cudaSetDevice(ba->e.device);
+  delete ba;
+}
+
+int stba_ba_set_state(stba_ba* ba, const double* q, const double* t, const double* lm) {
+  if (!ba || (ba->e.n_cam && (!q || !t)) || (ba->e.n_lm && !lm)) return STBA_ERR_INVALID_ARGUMENT;
+  return ba->e.set_state(q, t, lm);
+}
+int stba_ba_get_state(stba_ba* ba, double* q, double* t, double* lm) {
+  if (!ba) return STBA_ERR_INVALID_ARGUMENT;
+  return ba->e.get_state(q, t, lm);
+}
+
+int stba_ba_get_index(stba_ba* ba, int32_t* lm_deg, int32_t* cam_deg, int32_t* lm_ptr, int32_t* cam_ptr, int32_t* cam_perm) {
+  if (!ba) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  if (lm_deg && e.n_lm) CK(cudaMemcpy(lm_deg, e.lm_deg, e.n_lm * sizeof(int), cudaMemcpyDeviceToHost));
+  if (cam_deg && e.n_cam) CK(cudaMemcpy(cam_deg, e.cam_deg, e.n_cam * sizeof(int), cudaMemcpyDeviceToHost));
+  if (lm_ptr) CK(cudaMemcpy(lm_ptr, e.lm_ptr, ((size_t)e.n_lm + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  if (cam_ptr) CK(cudaMemcpy(cam_ptr, e.cam_ptr, ((size_t)e.n_cam + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  if (cam_perm && e.n_obs) CK(cudaMemcpy(cam_perm, e.cam_perm, e.n_obs * sizeof(int), cudaMemcpyDeviceToHost));
+  return STBA_OK;
+}
+
+int stba_ba_get_covis(stba_ba* ba, int64_t* keys, int64_t* n_keys) {
+  if (!ba || !n_keys) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  const int64_t np = (int64_t)e.n_cam * (e.n_cam - 1) / 2;
+  std::vector<uint8_t> h(std::max<int64_t>(np, 1), 0);
+  if (np > 0) {
+    uint8_t* map = nullptr;
+    CK(cudaMalloc(&map, np));
+    CK(cudaMemsetAsync(map, 0, np, e.stream));
+    if (e.n_lm) LAUNCH(&e, stba::k_covis_mark, e.grid_for(e.n_lm, 128), 128, e.n_lm, e.lm_ptr, e.obs_cam, map);
+    cudaError_t err = cudaMemcpyAsync(h.data(), map, np, cudaMemcpyDeviceToHost, e.stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e.stream);
+    cudaFree(map);
+    CK(err);
+  }
+  int64_t cnt = 0;
+  for (int64_t i = 1; i < e.n_cam; ++i)
+    for (int64_t j = 0; j < i; ++j)
+      if (h[i * (i - 1) / 2 + j]) {
+        if (keys) keys[cnt] = i * e.n_cam + j;
+        ++cnt;
+      }
+  *n_keys = cnt;
+  return STBA_OK;
+}
+
+int stba_ba_linearize(stba_ba* ba) {
+  if (!ba) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  CKR(e.linearize());
+  CK(cudaStreamSynchronize(e.stream));
+  return STBA_OK;
+}
+
+int stba_ba_get_blocks(stba_ba* ba, double* Hcc, double* gc, double* Hll, double* gl, double* cost) {
+  if (!ba || !ba->e.linearized) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  CK(cudaStreamSynchronize(e.stream));
+  if (Hcc && e.n_cam) CK(cudaMemcpy(Hcc, e.Hcc, 21 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToHost));
+  if (gc && e.n_cam) CK(cudaMemcpy(gc, e.gc, 6 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToHost));
+  if (Hll && e.n_lm) CK(cudaMemcpy(Hll, e.Hll, 6 * (size_t)e.n_lm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (gl && e.n_lm) CK(cudaMemcpy(gl, e.gl, 3 * (size_t)e.n_lm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cost) CK(cudaMemcpy(cost, e.scal + stba::SC_COST, sizeof(double), cudaMemcpyDeviceToHost));
+  return STBA_OK;
+}
+
+int stba_ba_reduced_system(stba_ba* ba, double radius, const stba_options* opt, double* S, double* rhs, int32_t* n) {
+  if (!ba || !(radius > 0)) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  stba_options o;
+  if (opt) o = *opt; else stba_options_init(&o);
+  CK(cudaSetDevice(e.device));
+  if (!e.linearized) CKR(e.linearize());
+  CKR(e.post_linearize(o, false));
+  CKR(e.build_reduced(radius, o));
+  CK(cudaStreamSynchronize(e.stream));
+  if (n) *n = e.n;
+  if (S && e.n) CK(cudaMemcpy(S, e.S, (size_t)e.n * e.n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (rhs && e.n) CK(cudaMemcpy(rhs, e.rhs, (size_t)e.n * sizeof(double), cudaMemcpyDeviceToHost));
+  return STBA_OK;
+}
+
+int stba_ba_solve_step(stba_ba* ba, int backend, double* yc, double* yl, double* mcc) {
+  if (!ba || !ba->e.reduced_built) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  CKR(e.dense_solve(backend));
+  CKR(e.step_from_solution());
+  CKR(e.candidate_cost());
+  CKR(e.fetch_scalars());
+  if (*e.info_host != 0) return STBA_ERR_SOLVER;
+  if (yc && e.n_cam) CK(cudaMemcpy(yc, e.yc, 6 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToHost));
+  if (yl && e.n_lm) CK(cudaMemcpy(yl, e.yl, 3 * (size_t)e.n_lm * sizeof(double), cudaMemcpyDeviceToHost));
+  if (mcc) *mcc = 0.5 * (e.scal_host[stba::SC_MCC_C] + e.scal_host[stba::SC_MCC_L]);
+  return STBA_OK;
+}
+
+int stba_ba_solve(stba_ba* ba, const stba_options* opt, stba_summary* summary, stba_iteration_callback cb, void* user) {
+  if (!ba) return STBA_ERR_INVALID_ARGUMENT;
+  stba_options o;
+  if (opt) o = *opt; else stba_options_init(&o);
+  return ba->e.solve(o, summary, cb, user);
+}
+
+int64_t stba_ba_launch_count(stba_ba* ba) { return ba ? ba->e.launches : 0; }
+
+int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms) {
+  if (!ba || reps < 1 || !ms || phase < 0 || phase > 6) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  stba_options o;
+  stba_options_init(&o);
+  if (flush_l2 && !e.flush_buf) {
+    e.flush_n = (size_t)192 << 20 >> 3;   // 192 MiB of doubles > 126 MB L2
+    CKR(e.alloc(&e.flush_buf, e.flush_n));
+  }
+  if (!e.linearized) { CKR(e.linearize()); CKR(e.post_linearize(o, false)); }
+  if (phase >= 4 || phase == 3) { if (!e.have_scale) CKR(e.post_linearize(o, false)); }
+  cudaEvent_t a = e.ev[0], b = e.ev[1];
+  for (int r = 0; r < reps; ++r) {
+    // preconditions of the phase, untimed
+    if (phase == 4 || phase == 5 || phase == 6) CKR(e.build_reduced(1e4, o));
+    if (phase == 5 || phase == 6) CKR(e.dense_solve(o.dense_backend));
+    if (phase == 6) CKR(e.step_from_solution());
+    if (flush_l2) stba::k_flush<<<e.sm_count * 8, 256, 0, e.stream>>>(e.flush_n, e.flush_buf, (double)r);
+    CK(cudaEventRecord(a, e.stream));
+    switch (phase) {
+      case 0: CKR(e.linearize()); break;
+      case 1:
+        LAUNCH(&e, (stba::k_lin_lm<false>), e.grid_for(e.n_lm, stba::kBlock), stba::kBlock, e.n_lm, e.lm_ptr, e.obs_cam, e.obs_uv,
+               e.Rt, e.lm4, e.Hll, e.gl, e.partial, e.counter, e.scal + stba::SC_COST);
+        break;
+      case 2:
+        if (e.n_chunk)
+          LAUNCH(&e, stba::k_lin_cam, e.grid_for(e.n_chunk, stba::kBlock / 32), stba::kBlock, e.n_chunk, e.chunk_cam, e.chunk_beg,
+                 e.chunk_end, e.cobs_lm, e.cobs_uv, e.Rt, e.lm4, e.chunk_acc);
+        LAUNCH(&e, stba::k_lin_cam_finish, (e.n_cam + 127) / 128, 128, e.n_cam, e.cam_chunk_ptr, e.cam_const, e.chunk_acc, e.Rt, e.Hcc, e.gc);
+        break;
+      case 3: CKR(e.build_reduced(1e4, o)); break;
+      case 4: CKR(e.dense_solve(o.dense_backend)); break;
+      case 5: CKR(e.step_from_solution()); break;
+      case 6: CKR(e.candidate_cost()); break;
+    }
+    CK(cudaEventRecord(b, e.stream));
+    CK(cudaStreamSynchronize(e.stream));
+    CK(cudaEventElapsedTime(&ms[r], a, b));
+  }
+  return STBA_OK;
+}
+
+
+int stba_ba_save_state(stba_ba* ba) {
+  if (!ba) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  if (!e.save_q) { CKR(e.alloc(&e.save_q, 4 * (size_t)e.n_cam)); CKR(e.alloc(&e.save_t, 3 * (size_t)e.n_cam)); CKR(e.alloc(&e.save_lm4, 4 * (size_t)e.n_lm)); }
+  CK(cudaMemcpyAsync(e.save_q, e.cam_q, 4 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  CK(cudaMemcpyAsync(e.save_t, e.cam_t, 3 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  CK(cudaMemcpyAsync(e.save_lm4, e.lm4, 4 * (size_t)e.n_lm * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  CK(cudaStreamSynchronize(e.stream));
+  return STBA_OK;
+}
+
+int stba_ba_restore_state(stba_ba* ba) {
+  if (!ba || !ba->e.save_q) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  CK(cudaMemcpyAsync(e.cam_q, e.save_q, 4 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  CK(cudaMemcpyAsync(e.cam_t, e.save_t, 3 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  CK(cudaMemcpyAsync(e.lm4, e.save_lm4, 4 * (size_t)e.n_lm * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
+  e.linearized = false; e.reduced_built = false;
+  return STBA_OK;
+}
+
+// fp64 FMA peak of this device: a register-resident DFMA chain, 8 independent accumulators per
+// thread.  Returns TFLOP/s (2 flops per FMA) of the best of `reps` launches.
+__global__ void k_dfma_peak(int iters, double seed, double* out) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 12345.678) out[0] = r;
+}
+
+int stba_peak_fp64(int device, int reps, double* tflops) {
+  if (!tflops || reps < 1) return STBA_ERR_INVALID_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STBA_ERR_NO_DEVICE; }
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double* out = nullptr;
+  CK(cudaMalloc(&out, sizeof(double)));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  const int iters = 1 << 15, grid = prop.multiProcessorCount * 8, block = 256;
+  double best = 0.0;
+  for (int r = 0; r < reps + 1; ++r) {
+    CK(cudaEventRecord(a));
+    k_dfma_peak<<<grid, block>>>(iters, 1.0 + r, out);
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    const double tf = 2.0 * 8.0 * iters * (double)grid * block / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+  *tflops = best;
+  return STBA_OK;
+}
+
+int stba_comm_unique_id(char* id_out) {
+  if (!id_out) return STBA_ERR_INVALID_ARGUMENT;
+  static_assert(sizeof(ncclUniqueId) <= STBA_UNIQUE_ID_BYTES, "unique id size");
+  ncclUniqueId id;
+  CKN(ncclGetUniqueId(&id));
+  memset(id_out, 0, STBA_UNIQUE_ID_BYTES);
+  memcpy(id_out, &id, sizeof(id));
+  return STBA_OK;
+}
+
+int stba_ba_comm_init(stba_ba* ba, int rank, int nranks, const char* id) {
+  if (!ba || !id || nranks < 1 || rank < 0 || rank >= nranks) return STBA_ERR_INVALID_ARGUMENT;
+  Engine& e = ba->e;
+  CK(cudaSetDevice(e.device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  CKN(ncclCommInitRank(&e.comm, nranks, uid, rank));
+  e.rank = rank;
+  e.nranks = nranks;
+  return STBA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,10 @@
+"""Importable alias for the ``slam-tricks_b200`` package (hyphenated directory name)."""
+import importlib
+import os
+import sys
+
+_here = os.path.dirname(os.path.abspath(__file__))
+if _here not in sys.path:
+    sys.path.insert(0, _here)
+_pkg = importlib.import_module("slam-tricks_b200")
+sys.modules[__name__] = _pkg
