@@ -199,6 +199,12 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
 /* kernels launched on this handle since creation */
 int64_t stba_ba_launch_count(stba_ba* ba);
 
+/* Stand-alone entry to the dense back ends (tests, micro-benchmarks): solve S x = rhs with S a
+ * HOST column-major n x n matrix of which the lower triangle is read.  info follows LAPACK potrf.
+ * ms (nullable) receives `reps` device times (factor + solve on a fresh copy of S each). */
+int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, const double* rhs,
+                              double* x, int* info, int reps, float* ms);
+
 /* Multi-GPU: landmark-sharded, one handle per rank holding ALL cameras and its own landmarks /
  * observations; one ncclAllReduce of [S | rhs | scalars] per linearisation. */
 #define STBA_UNIQUE_ID_BYTES 128

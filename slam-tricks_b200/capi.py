@@ -107,6 +107,7 @@ SIGNATURES = {
     "stba_ba_solve": (C.c_int, [C.c_void_p, C.POINTER(Options), C.POINTER(SummaryStruct), ITERATION_CALLBACK, C.c_void_p]),
     "stba_ba_time_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "stba_ba_launch_count": (C.c_int64, [C.c_void_p]),
+    "stba_dense_cholesky_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _ip, C.c_int, C.POINTER(C.c_float)]),
     "stba_comm_unique_id": (C.c_int, [C.c_char_p]),
     "stba_ba_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     "stba_problem_create": (C.c_int, [C.POINTER(C.c_void_p)]),

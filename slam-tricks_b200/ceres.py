@@ -93,19 +93,23 @@ class Problem:
         return a.ctypes.data
 
     def AddParameterBlock(self, values, size, local_parameterization=None):
+        self._flush()
         m = local_parameterization.manifold if local_parameterization is not None else capi.MANIFOLD_EUCLIDEAN
         capi.check(self._L.stba_problem_add_parameter_block(self._h, self._addr(values), int(size), m),
                    "stba_problem_add_parameter_block")
 
     def SetParameterBlockConstant(self, values):
+        self._flush()
         capi.check(self._L.stba_problem_set_parameter_block_constant(self._h, self._addr(values)),
                    "stba_problem_set_parameter_block_constant")
 
     def SetParameterLowerBound(self, values, index, bound):
+        self._flush()
         capi.check(self._L.stba_problem_set_parameter_lower_bound(self._h, self._addr(values), index, bound),
                    "stba_problem_set_parameter_lower_bound")
 
     def SetParameterUpperBound(self, values, index, bound):
+        self._flush()
         capi.check(self._L.stba_problem_set_parameter_upper_bound(self._h, self._addr(values), index, bound),
                    "stba_problem_set_parameter_upper_bound")
 

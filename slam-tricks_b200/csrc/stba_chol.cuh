@@ -7,9 +7,10 @@
 
 namespace stba {
 
+struct CholPlan;
 struct CholWorkspace {
-  double* buf = nullptr;   // allocated lazily by chol_factor_solve
-  size_t bytes = 0;
+  CholPlan* plan = nullptr;   // captured schedule + side buffers for one (S, n); built lazily
+  ~CholWorkspace();
 };
 
 // In-place lower Cholesky of the column-major n x n matrix S (leading dimension n) followed by

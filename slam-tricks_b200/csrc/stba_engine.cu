@@ -226,7 +226,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CKR(alloc(&Linv, 6 * (size_t)nlm)); CKR(alloc(&hl, 3 * (size_t)nlm));
   CKR(alloc(&yc, 6 * (size_t)ncam)); CKR(alloc(&yl, 3 * (size_t)nlm));
   CKR(alloc(&partial, (size_t)max_grid * 8)); CKR(alloc(&counter, 1)); CKR(alloc(&scal, SC_COUNT));
-  CKR(alloc(&dev_info, 1)); CKR(alloc(&dup_flag, 1));
+  CKR(alloc(&dev_info, 2)); CKR(alloc(&dup_flag, 1));   // dev_info[1]: potrs' own status (it would overwrite potrf's)
   CK(cudaMallocHost(&scal_host, SC_COUNT * sizeof(double)));
   CK(cudaMallocHost(&info_host, sizeof(int)));
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
@@ -293,12 +293,6 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CKR(alloc(&E, 18 * (size_t)nobs));
   CKR(alloc(&S, (size_t)n * n)); CKR(alloc(&rhs, (size_t)n));
   CK(cudaMemsetAsync(S, 0, std::max<size_t>((size_t)n * n, 1) * sizeof(double), stream));
-  if (cusolverDnCreate(&cusolver) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
-  CKS(cusolverDnSetStream(cusolver, stream));
-  if (n > 0) {
-    CKS(cusolverDnDpotrf_bufferSize(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, n, &potrf_lwork));
-    CKR(alloc(&potrf_work, (size_t)potrf_lwork));
-  }
   CK(cudaStreamSynchronize(stream));
   return STBA_OK;
 }
@@ -433,8 +427,14 @@ int Engine::dense_solve(int backend) {
   CK(cudaMemsetAsync(dev_info, 0, sizeof(int), stream));
   if (n > 0) {
     if (backend == STBA_DENSE_CUSOLVER) {
+      if (!cusolver) {   // created on first use: loading cuSOLVER costs tens of milliseconds
+        if (cusolverDnCreate(&cusolver) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
+        CKS(cusolverDnSetStream(cusolver, stream));
+        CKS(cusolverDnDpotrf_bufferSize(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, n, &potrf_lwork));
+        CKR(alloc(&potrf_work, (size_t)potrf_lwork));
+      }
       CKS(cusolverDnDpotrf(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, n, potrf_work, potrf_lwork, dev_info));
-      CKS(cusolverDnDpotrs(cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, S, n, rhs, n, dev_info));
+      CKS(cusolverDnDpotrs(cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, S, n, rhs, n, dev_info + 1));
       launches += 2;
     } else {
       int nl = 0;
@@ -935,6 +935,63 @@ int stba_peak_fp64(int device, int reps, double* tflops) {
   cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
   *tflops = best;
   return STBA_OK;
+}
+
+// Stand-alone entry to the dense back ends (tests / micro-benchmarks): solves S x = rhs for a
+// host matrix (column-major, lower triangle read).  ms (nullable) receives `reps` device times of
+// factor + solve, each on a fresh copy of S.
+int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, const double* rhs, double* x, int* info,
+                              int reps, float* ms) {
+  if (n < 0 || (n && (!S || !rhs || !x)) || reps < 1) return STBA_ERR_INVALID_ARGUMENT;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STBA_ERR_NO_DEVICE; }
+  CK(cudaSetDevice(device));
+  if (n == 0) { if (info) *info = 0; return STBA_OK; }
+  double *dS = nullptr, *dS0 = nullptr, *dr = nullptr, *dr0 = nullptr, *work = nullptr;
+  int* dinfo = nullptr;
+  cudaStream_t st;
+  cudaEvent_t a, b;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  const size_t bytes = (size_t)n * n * sizeof(double);
+  CK(cudaMalloc(&dS, bytes)); CK(cudaMalloc(&dS0, bytes)); CK(cudaMalloc(&dr, n * sizeof(double))); CK(cudaMalloc(&dr0, n * sizeof(double)));
+  CK(cudaMalloc(&dinfo, 2 * sizeof(int)));
+  CK(cudaMemcpy(dS0, S, bytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dr0, rhs, n * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = STBA_OK;
+  cusolverDnHandle_t h = nullptr;
+  int lwork = 0;
+  stba::CholWorkspace ws;
+  if (backend == STBA_DENSE_CUSOLVER) {
+    if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
+    CKS(cusolverDnSetStream(h, st));
+    CKS(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, n, dS, n, &lwork));
+    CK(cudaMalloc(&work, std::max(lwork, 1) * sizeof(double)));
+  }
+  for (int r = 0; r < reps && rc == STBA_OK; ++r) {
+    CK(cudaMemcpyAsync(dS, dS0, bytes, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(dr, dr0, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(dinfo, 0, sizeof(int), st));
+    CK(cudaEventRecord(a, st));
+    if (backend == STBA_DENSE_CUSOLVER) {
+      CKS(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, n, dS, n, work, lwork, dinfo));
+      CKS(cusolverDnDpotrs(h, CUBLAS_FILL_MODE_LOWER, n, 1, dS, n, dr, n, dinfo + 1));
+    } else {
+      int nl = 0;
+      rc = stba::chol_factor_solve(ws, dS, n, dr, dinfo, st, &nl);
+    }
+    CK(cudaEventRecord(b, st));
+    CK(cudaStreamSynchronize(st));
+    if (ms) CK(cudaEventElapsedTime(&ms[r], a, b));
+  }
+  if (rc == STBA_OK) {
+    CK(cudaMemcpy(x, dr, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (info) CK(cudaMemcpy(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  if (h) cusolverDnDestroy(h);
+  cudaFree(dS); cudaFree(dS0); cudaFree(dr); cudaFree(dr0); cudaFree(dinfo); if (work) cudaFree(work);
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(st);
+  return rc;
 }
 
 int stba_comm_unique_id(char* id_out) {

@@ -167,6 +167,17 @@ class BAEngine:
         capi.check(self._L.stba_ba_comm_init(self._h, rank, nranks, unique_id), "stba_ba_comm_init")
 
 
+def dense_cholesky_solve(S, rhs, backend=capi.DENSE_OWN, reps=1, device=0):
+    """Solve S x = rhs on the GPU with one of the dense back ends (S symmetric: lower triangle read).
+    Returns (x, info, ms[reps])."""
+    S = np.asfortranarray(S, dtype=np.float64); rhs = capi.as_f64(rhs)
+    n = S.shape[0]
+    x = np.empty(n); info = C.c_int32(0); ms = (C.c_float * reps)()
+    capi.check(capi.lib().stba_dense_cholesky_solve(device, backend, n, S.ctypes.data_as(C.POINTER(C.c_double)), capi.dptr(rhs),
+                                                    capi.dptr(x), C.byref(info), reps, ms), "stba_dense_cholesky_solve")
+    return x, info.value, np.array(list(ms))
+
+
 def peak_fp64(device=0, reps=5):
     v = C.c_double(0)
     capi.check(capi.lib().stba_peak_fp64(device, reps, C.byref(v)), "stba_peak_fp64")

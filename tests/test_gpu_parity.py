@@ -136,14 +136,23 @@ def test_full_lm_solve_matches_oracle(stba, bo, fix, backend, request):
 
 
 def test_rejected_steps_follow_the_oracle(stba, bo):
-    # a hard start (large noise, small radius) exercises the reject / radius-shrink branch
-    sc = stba.synth.make_scene(20, 300, 1200, pos_noise=1.0, angle_noise_deg=12.0, lm_noise=0.5)
-    o = bo.LMOptions(initial_trust_region_radius=1e6)
-    want = bo.solve(*scene_args(sc), options=o)
-    assert any(not it["step_is_successful"] for it in want[3].iterations), "test scene no longer produces a rejected step"
+    # a hard start (large noise) exercises the reject / radius-shrink / diagonal-reuse branch.
+    # Far from the minimum, through repeated rejections, the path is chaotic: rounding-level
+    # differences (the oracle scales the Jacobian, the kernels scale the LM diagonal) grow to
+    # ~1e-7, so this test checks the DECISIONS exactly and the values to 1e-5, over 8 iterations.
+    sc = stba.synth.make_scene(20, 300, 1200, pos_noise=1.5, angle_noise_deg=20.0, lm_noise=1.0)
+    want = bo.solve(*scene_args(sc), options=bo.LMOptions(max_num_iterations=8))
+    flags = [bool(it["step_is_successful"]) for it in want[3].iterations]
+    assert flags.count(False) >= 2, "test scene no longer produces rejected steps"
     with _engine(stba, sc) as e:
-        summ = e.solve(stba.capi.Options(initial_trust_region_radius=1e6))
-        _compare_solutions(bo, sc, e.get_state(), summ, want)
+        summ = e.solve(stba.capi.Options(max_num_iterations=8))
+        q, t, l = e.get_state()
+    assert summ.termination_type == want[3].termination_type == "NO_CONVERGENCE"
+    assert [bool(it["step_is_successful"]) for it in summ.iterations] == flags
+    for a, b in zip(summ.iterations, want[3].iterations):
+        assert abs(a["cost"] - b["cost"]) <= 1e-5 * b["cost"]
+        assert abs(a["trust_region_radius"] - b["trust_region_radius"]) <= 1e-5 * b["trust_region_radius"]
+    assert np.max(np.abs(q - want[0])) < 1e-4 and np.max(np.abs(t - want[1])) < 1e-4 and np.max(np.abs(l - want[2])) < 1e-3
 
 
 def test_ceres_front_door_reproduces_engine_and_oracle(stba, bo, scene_small):
@@ -261,3 +270,27 @@ def test_config_C_full_solve_against_golden(stba, scene_C):
         assert abs(a.sum() - g["sum"]) <= 1e-5 * max(1.0, abs(g["sum"])) * np.sqrt(a.size)
         idx = np.asarray(g["sample_index"])
         assert np.max(np.abs(a.reshape(-1)[idx] - np.asarray(g["sample"]))) <= 1e-5
+
+
+# ---- the dense reduced-camera solve in isolation -----------------------------------------------
+@pytest.mark.parametrize("n", [6, 30, 126, 128, 132, 258, 1002, 2994])
+@pytest.mark.parametrize("backend", ["own", "cusolver"])
+def test_dense_cholesky_solve(stba, n, backend):
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(n, n + 8))
+    S = A @ A.T + 1e-3 * n * np.eye(n)
+    x_true = rng.normal(size=n)
+    rhs = S @ x_true
+    be = stba.capi.DENSE_OWN if backend == "own" else stba.capi.DENSE_CUSOLVER
+    x, info, _ = stba.engine.dense_cholesky_solve(np.tril(S), rhs, be)
+    assert info == 0
+    x_ref = np.linalg.solve(S, rhs)
+    assert np.max(np.abs(x - x_ref)) <= 1e-9 * np.max(np.abs(x_ref)) * max(1.0, np.linalg.cond(S) * 1e-6)
+    assert np.linalg.norm(S @ x - rhs) <= 1e-11 * np.linalg.norm(rhs)
+
+
+def test_dense_cholesky_reports_indefinite_matrix(stba):
+    S = np.eye(300); S[200, 200] = -1.0
+    for be in (stba.capi.DENSE_OWN, stba.capi.DENSE_CUSOLVER):
+        _, info, _ = stba.engine.dense_cholesky_solve(S, np.ones(300), be)
+        assert info == 201
