@@ -243,13 +243,14 @@ def main():
                     "launch_ms": float(ms.mean()), "l2": "flushed between repetitions (192 MiB write sweep)"}
         fp64 = stba.engine.peak_fp64(local)
         n = 6 * int((d["cam_const"] == 0).sum())
-        dms = eng.time_phase("dense", reps=5)[1:]
+        dense_phase = "dense_own" if opt.dense_backend == stba.capi.DENSE_OWN else "dense_cusolver"
+        dms = eng.time_phase(dense_phase, reps=5)[1:]
         extra["roofline_dense"] = {"bound": "fp64", "kernel": "reduced-camera Cholesky + solve (n=%d)" % n, "achieved": (n ** 3 / 3 + 2 * n * n) / (dms.mean() * 1e-3) / 1e12,
                                    "peak": fp64, "unit": "TFLOP/s", "peak_source": "stba_peak_fp64 (DFMA chains, measured in this run)",
                                    "launch_ms": float(dms.mean())}
         extra["roofline_dense"]["frac"] = extra["roofline_dense"]["achieved"] / fp64 if fp64 else None
         extra["phase_ms_per_solve"] = {k: v for k, v in last.phase_ms.items()}
-        extra["phase_ms_isolated"] = {ph: float(eng.time_phase(ph, reps=5)[1:].mean()) for ph in ("lin_lm", "lin_cam", "schur", "dense", "backsub", "cost")}
+        extra["phase_ms_isolated"] = {ph: float(eng.time_phase(ph, reps=5)[1:].mean()) for ph in ("lin_lm", "lin_cam", "schur", "dense_own", "dense_cusolver", "backsub", "cost")}
         extra["iterations_per_solve"] = n_iters(last)
         extra["termination"] = last.termination_type
         extra["final_cost"] = last.final_cost

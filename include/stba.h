@@ -192,7 +192,8 @@ int stba_ba_solve(stba_ba* ba, const stba_options* opt, stba_summary* summary,
 
 /* Timing helpers (CUDA events on the engine's own stream; warm-up is the caller's job).
  * phase: 0 = linearise (lin_lm + lin_cam), 1 = lin_lm only, 2 = lin_cam only, 3 = schur build,
- * 4 = dense factor+solve, 5 = back-substitution+update, 6 = candidate cost.
+ * 4 = dense factor+solve (default back end), 5 = back-substitution+update, 6 = candidate cost,
+ * 7 = dense with STBA_DENSE_OWN, 8 = dense with STBA_DENSE_CUSOLVER.
  * Writes `reps` per-launch durations in milliseconds; flush_l2 != 0 rewrites a >L2 buffer
  * between repetitions (outside the timed region). */
 int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms);

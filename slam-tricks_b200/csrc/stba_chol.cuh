@@ -13,10 +13,10 @@ struct CholWorkspace {
   ~CholWorkspace();
 };
 
-// In-place lower Cholesky of the column-major n x n matrix S (leading dimension n) followed by
-// the two triangular solves on rhs (n).  dev_info <- 0 on success, k > 0 if the leading minor k
+// In-place lower Cholesky of the column-major n x n matrix S (leading dimension ld >= n + 1, ld even:
+// row n of S is scratch for the right-hand side) followed by the two triangular solves on rhs (n).  dev_info <- 0 on success, k > 0 if the leading minor k
 // is not positive definite (LAPACK convention).  *n_launches += kernels launched.
-int chol_factor_solve(CholWorkspace& ws, double* S, int n, double* rhs, int* dev_info, cudaStream_t stream,
+int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream,
                       int* n_launches);
 
 }  // namespace stba

@@ -72,7 +72,7 @@ enum Phase { PH_LIN = 0, PH_SCHUR, PH_DENSE, PH_BACKSUB, PH_COST, PH_COUNT };
 struct Engine {
   int device = 0;
   cudaStream_t stream = nullptr;
-  int n_cam = 0, n_lm = 0, n_free = 0, n = 0;  // n = 6 * n_free
+  int n_cam = 0, n_lm = 0, n_free = 0, n = 0, ld = 0;  // n = 6 * n_free; ld = n + 2 (row n: rhs scratch of the own Cholesky)
   int64_t n_obs = 0, n_blk = 0, n_inc = 0;
   int n_chunk = 0, chunk_size = 0, sm_count = 148, max_grid = 148 * 16;
   int64_t launches = 0;
@@ -206,6 +206,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
     h_free[c] = h_const[c] ? -1 : n_free++;
   }
   n = 6 * n_free;
+  ld = n + 2;
   has_lm_const = false;
   if (h_lc) for (int l = 0; l < nlm; ++l) if (h_lc[l]) { has_lm_const = true; break; }
 
@@ -291,8 +292,8 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
 
   // ---- Schur / dense workspaces ----
   CKR(alloc(&E, 18 * (size_t)nobs));
-  CKR(alloc(&S, (size_t)n * n)); CKR(alloc(&rhs, (size_t)n));
-  CK(cudaMemsetAsync(S, 0, std::max<size_t>((size_t)n * n, 1) * sizeof(double), stream));
+  CKR(alloc(&S, (size_t)ld * n)); CKR(alloc(&rhs, (size_t)n));
+  CK(cudaMemsetAsync(S, 0, std::max<size_t>((size_t)ld * n, 1) * sizeof(double), stream));
   CK(cudaStreamSynchronize(stream));
   return STBA_OK;
 }
@@ -405,15 +406,15 @@ int Engine::build_reduced(double radius, const stba_options& opt) {
   if (n_free) {
     if (n_chunk)
       LAUNCH(this, k_schur_diag, grid_for(n_chunk, kBlock / 32), kBlock, n_chunk, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
-    LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, S, n, rhs,
+    LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, S, ld, rhs,
            nranks > 1 ? 0 : 1);
-    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, S, n);
+    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, S, ld);
     if (nranks > 1) {
       CKN(ncclGroupStart());
-      CKN(ncclAllReduce(S, S, (size_t)n * n, ncclDouble, ncclSum, comm, stream));
+      CKN(ncclAllReduce(S, S, (size_t)ld * n, ncclDouble, ncclSum, comm, stream));
       CKN(ncclAllReduce(rhs, rhs, (size_t)n, ncclDouble, ncclSum, comm, stream));
       CKN(ncclGroupEnd());
-      LAUNCH(this, k_add_cam_blocks, (n_cam + 127) / 128, 128, n_cam, free_of, Hcc, gc, Dc2, S, n, rhs);
+      LAUNCH(this, k_add_cam_blocks, (n_cam + 127) / 128, 128, n_cam, free_of, Hcc, gc, Dc2, S, ld, rhs);
     }
   }
   CK(cudaGetLastError());
@@ -430,15 +431,15 @@ int Engine::dense_solve(int backend) {
       if (!cusolver) {   // created on first use: loading cuSOLVER costs tens of milliseconds
         if (cusolverDnCreate(&cusolver) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
         CKS(cusolverDnSetStream(cusolver, stream));
-        CKS(cusolverDnDpotrf_bufferSize(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, n, &potrf_lwork));
+        CKS(cusolverDnDpotrf_bufferSize(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, ld, &potrf_lwork));
         CKR(alloc(&potrf_work, (size_t)potrf_lwork));
       }
-      CKS(cusolverDnDpotrf(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, n, potrf_work, potrf_lwork, dev_info));
-      CKS(cusolverDnDpotrs(cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, S, n, rhs, n, dev_info + 1));
+      CKS(cusolverDnDpotrf(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, ld, potrf_work, potrf_lwork, dev_info));
+      CKS(cusolverDnDpotrs(cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, S, ld, rhs, n, dev_info + 1));
       launches += 2;
     } else {
       int nl = 0;
-      CKR(chol_factor_solve(chol, S, n, rhs, dev_info, stream, &nl));
+      CKR(chol_factor_solve(chol, S, n, ld, rhs, dev_info, stream, &nl));
       launches += nl;
     }
   }
@@ -799,7 +800,7 @@ int stba_ba_reduced_system(stba_ba* ba, double radius, const stba_options* opt, 
   CKR(e.build_reduced(radius, o));
   CK(cudaStreamSynchronize(e.stream));
   if (n) *n = e.n;
-  if (S && e.n) CK(cudaMemcpy(S, e.S, (size_t)e.n * e.n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (S && e.n) CK(cudaMemcpy2D(S, (size_t)e.n * sizeof(double), e.S, (size_t)e.ld * sizeof(double), (size_t)e.n * sizeof(double), e.n, cudaMemcpyDeviceToHost));
   if (rhs && e.n) CK(cudaMemcpy(rhs, e.rhs, (size_t)e.n * sizeof(double), cudaMemcpyDeviceToHost));
   return STBA_OK;
 }
@@ -829,7 +830,7 @@ int stba_ba_solve(stba_ba* ba, const stba_options* opt, stba_summary* summary, s
 int64_t stba_ba_launch_count(stba_ba* ba) { return ba ? ba->e.launches : 0; }
 
 int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms) {
-  if (!ba || reps < 1 || !ms || phase < 0 || phase > 6) return STBA_ERR_INVALID_ARGUMENT;
+  if (!ba || reps < 1 || !ms || phase < 0 || phase > 8) return STBA_ERR_INVALID_ARGUMENT;
   Engine& e = ba->e;
   CK(cudaSetDevice(e.device));
   stba_options o;
@@ -843,7 +844,7 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
   cudaEvent_t a = e.ev[0], b = e.ev[1];
   for (int r = 0; r < reps; ++r) {
     // preconditions of the phase, untimed
-    if (phase == 4 || phase == 5 || phase == 6) CKR(e.build_reduced(1e4, o));
+    if (phase == 4 || phase == 5 || phase == 6 || phase == 7 || phase == 8) CKR(e.build_reduced(1e4, o));
     if (phase == 5 || phase == 6) CKR(e.dense_solve(o.dense_backend));
     if (phase == 6) CKR(e.step_from_solution());
     if (flush_l2) stba::k_flush<<<e.sm_count * 8, 256, 0, e.stream>>>(e.flush_n, e.flush_buf, (double)r);
@@ -862,6 +863,8 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
         break;
       case 3: CKR(e.build_reduced(1e4, o)); break;
       case 4: CKR(e.dense_solve(o.dense_backend)); break;
+      case 7: CKR(e.dense_solve(STBA_DENSE_OWN)); break;
+      case 8: CKR(e.dense_solve(STBA_DENSE_CUSOLVER)); break;
       case 5: CKR(e.step_from_solution()); break;
       case 6: CKR(e.candidate_cost()); break;
     }
@@ -953,10 +956,12 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
   cudaEvent_t a, b;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-  const size_t bytes = (size_t)n * n * sizeof(double);
+  const int ld = n + 2;
+  const size_t bytes = (size_t)ld * n * sizeof(double);
   CK(cudaMalloc(&dS, bytes)); CK(cudaMalloc(&dS0, bytes)); CK(cudaMalloc(&dr, n * sizeof(double))); CK(cudaMalloc(&dr0, n * sizeof(double)));
   CK(cudaMalloc(&dinfo, 2 * sizeof(int)));
-  CK(cudaMemcpy(dS0, S, bytes, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dS0, 0, bytes));
+  CK(cudaMemcpy2D(dS0, (size_t)ld * sizeof(double), S, (size_t)n * sizeof(double), (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dr0, rhs, n * sizeof(double), cudaMemcpyHostToDevice));
   int rc = STBA_OK;
   cusolverDnHandle_t h = nullptr;
@@ -965,7 +970,7 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
   if (backend == STBA_DENSE_CUSOLVER) {
     if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
     CKS(cusolverDnSetStream(h, st));
-    CKS(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, n, dS, n, &lwork));
+    CKS(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, n, dS, ld, &lwork));
     CK(cudaMalloc(&work, std::max(lwork, 1) * sizeof(double)));
   }
   for (int r = 0; r < reps && rc == STBA_OK; ++r) {
@@ -974,11 +979,11 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
     CK(cudaMemsetAsync(dinfo, 0, sizeof(int), st));
     CK(cudaEventRecord(a, st));
     if (backend == STBA_DENSE_CUSOLVER) {
-      CKS(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, n, dS, n, work, lwork, dinfo));
-      CKS(cusolverDnDpotrs(h, CUBLAS_FILL_MODE_LOWER, n, 1, dS, n, dr, n, dinfo + 1));
+      CKS(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, n, dS, ld, work, lwork, dinfo));
+      CKS(cusolverDnDpotrs(h, CUBLAS_FILL_MODE_LOWER, n, 1, dS, ld, dr, n, dinfo + 1));
     } else {
       int nl = 0;
-      rc = stba::chol_factor_solve(ws, dS, n, dr, dinfo, st, &nl);
+      rc = stba::chol_factor_solve(ws, dS, n, ld, dr, dinfo, st, &nl);
     }
     CK(cudaEventRecord(b, st));
     CK(cudaStreamSynchronize(st));

@@ -153,7 +153,7 @@ class BAEngine:
         return run_solve(self._L.stba_ba_solve, self._h, options, callback)
 
     # ---- timing ----
-    PHASES = dict(linearize=0, lin_lm=1, lin_cam=2, schur=3, dense=4, backsub=5, cost=6)
+    PHASES = dict(linearize=0, lin_lm=1, lin_cam=2, schur=3, dense=4, backsub=5, cost=6, dense_own=7, dense_cusolver=8)
 
     def time_phase(self, phase, reps=10, flush_l2=False):
         ms = (C.c_float * reps)()
