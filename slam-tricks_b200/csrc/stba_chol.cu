@@ -456,6 +456,7 @@ static void destroy_plan(CholPlan* p) {
 }
 
 CholWorkspace::~CholWorkspace() { destroy_plan(plan); }
+void CholWorkspace::reset() { destroy_plan(plan); plan = nullptr; }
 
 // Enqueue the whole factor + solve schedule on `main` (and `side` for the look-ahead panels).
 static int enqueue(CholPlan& P, cudaStream_t main, bool lookahead) {

@@ -11,6 +11,7 @@ struct CholPlan;
 struct CholWorkspace {
   CholPlan* plan = nullptr;   // captured schedule + side buffers for one (S, n); built lazily
   ~CholWorkspace();
+  void reset();               // drop the captured schedule (before its buffers are freed)
 };
 
 // In-place lower Cholesky of the column-major n x n matrix S (leading dimension ld >= n + 1, ld even:

@@ -11,8 +11,11 @@
 
 namespace stba {
 
-// camera tile: R row-major (9) + t (3) = 12 doubles = 96 B, 16-byte aligned
-constexpr int kCamTile = 12;
+// camera tile: R row-major (9) + t (3) = 12 doubles, stored with a stride of 14 doubles (112 B =
+// 7 x 16 B): odd multiple of 16 B, so that random tiles spread over all shared-memory bank groups
+// when the table is staged in shared memory, and every tile stays 16-byte aligned.
+constexpr int kCamTile = 14;
+constexpr int kCamVals = 12;
 
 struct Obs {          // everything one observation contributes, in the CAMERA frame
   double u, v, iz;    // projection and 1/z
@@ -108,6 +111,32 @@ __device__ __forceinline__ void quat_mul_normalized(const double* a, const doubl
   o[1] = y * inv;
   o[2] = z * inv;
   o[3] = w * inv;
+}
+
+// ---- TMA 1-D bulk copy (cp.async.bulk) + mbarrier helpers -----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` (bytes: multiple of 16, 16-byte aligned both sides)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // ---- block reductions -----------------------------------------------------------------------

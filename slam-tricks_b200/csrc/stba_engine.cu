@@ -5,6 +5,7 @@
 #include <nccl.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -18,6 +19,7 @@
 #include "../../include/stba.h"
 #include "stba_chol.cuh"
 #include "stba_kernels.cuh"
+#include "stba_lin.cuh"
 
 namespace stba {
 
@@ -51,6 +53,18 @@ namespace stba {
     int r_ = (call);              \
     if (r_ != STBA_OK) return r_; \
   } while (0)
+
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  Trace() : on(getenv("STBA_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[stba trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 enum Scalar {
   SC_COST = 0,   // 1/2 |r|^2 at x (this rank's landmarks)
@@ -111,11 +125,14 @@ struct Engine {
   int rank = 0, nranks = 1;
   std::vector<void*> allocs;
 
+  // Stream-ordered allocation from the device's default memory pool, whose release threshold is
+  // raised once per process (process_init): freed blocks stay cached, so building the next problem
+  // costs microseconds instead of the ~10-60 ms that ~50 cudaMalloc calls of up to 290 MB take.
   template <typename T>
   int alloc(T** p, size_t count) {
     *p = nullptr;
     void* q = nullptr;
-    CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    CK(cudaMallocAsync(&q, std::max<size_t>(count, 1) * sizeof(T), stream));
     allocs.push_back(q);
     *p = static_cast<T*>(q);
     return STBA_OK;
@@ -125,11 +142,12 @@ struct Engine {
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, max_grid));
   }
   ~Engine() {
-    if (stream) cudaStreamSynchronize(stream);
-    for (void* p : allocs) cudaFree(p);
+    chol.reset();   // the captured graph references this engine's buffers
+    if (stream) {
+      for (void* p : allocs) cudaFreeAsync(p, stream);
+      cudaStreamSynchronize(stream);
+    }
     if (scal_host) cudaFreeHost(scal_host);
-    if (info_host) cudaFreeHost(info_host);
-    if (cusolver) cusolverDnDestroy(cusolver);
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
     if (comm) ncclCommDestroy(comm);
@@ -153,6 +171,33 @@ struct Engine {
   int allreduce_max(double* p, size_t count);
   int solve(const stba_options& opt, stba_summary* sum, stba_iteration_callback cb, void* user);
 };
+
+// once per process and device: device properties, kernel attributes, memory-pool policy, and the
+// cuSOLVER handle of the yard-stick back end (cusolverDnCreate alone costs ~15 ms)
+struct DeviceCtx {
+  bool ready = false;
+  int sm_count = 148;
+  cusolverDnHandle_t cusolver = nullptr;
+};
+static DeviceCtx g_dev[64];
+
+static int process_init(int device) {
+  DeviceCtx& d = g_dev[device];
+  if (d.ready) return STBA_OK;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  d.sm_count = prop.multiProcessorCount;
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long keep = ~0ull;
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  CK(cudaFuncSetAttribute(k_lin_lm2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmemBytes));
+  CK(cudaFuncSetAttribute(k_lin_lm2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmemBytes));
+  CK(cudaFuncSetAttribute(k_lin_lm2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmemBytes));
+  CK(cudaFuncSetAttribute(k_lin_lm2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmemBytes));
+  d.ready = true;
+  return STBA_OK;
+}
 
 #define LAUNCH(e, kernel, grid, block, ...)                   \
   do {                                                        \
@@ -179,24 +224,27 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
     return STBA_ERR_INVALID_ARGUMENT;
   if ((ncam && (!h_q || !h_t)) || (nlm && !h_lm) || (nobs && (!h_oc || !h_ol || !h_uv)))
     return STBA_ERR_INVALID_ARGUMENT;
+  Trace tr;
   // host-side validation of the ordering contract (test_ceres.h:109-110: landmark-major)
   for (int64_t i = 0; i < nobs; ++i) {
     if (h_oc[i] < 0 || h_oc[i] >= ncam || h_ol[i] < 0 || h_ol[i] >= nlm) return STBA_ERR_INVALID_ARGUMENT;
     if (i && h_ol[i] < h_ol[i - 1]) return STBA_ERR_INVALID_ARGUMENT;
   }
+  tr.mark("validate");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STBA_ERR_NO_DEVICE; }
   if (dev < 0 || dev >= ndev) return STBA_ERR_INVALID_ARGUMENT;
   device = dev;
   CK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  sm_count = prop.multiProcessorCount;
+  if (dev >= 64) return STBA_ERR_INVALID_ARGUMENT;
+  CKR(process_init(device));
+  sm_count = g_dev[device].sm_count;
   max_grid = sm_count * 16;
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto& e : ev) CK(cudaEventCreate(&e));
   n_cam = ncam; n_lm = nlm; n_obs = nobs;
 
+  tr.mark("stream/events/attrs");
   // ---- free-camera map (host) ----
   std::vector<int> h_free(std::max(ncam, 1), -1);
   std::vector<uint8_t> h_const(std::max(ncam, 1), 0);
@@ -214,7 +262,8 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CKR(alloc(&cam_q, 4 * (size_t)ncam)); CKR(alloc(&cam_t, 3 * (size_t)ncam)); CKR(alloc(&lm4, 4 * (size_t)nlm));
   CKR(alloc(&cam_q2, 4 * (size_t)ncam)); CKR(alloc(&cam_t2, 3 * (size_t)ncam)); CKR(alloc(&lm4_2, 4 * (size_t)nlm));
   CKR(alloc(&Rt, kCamTile * (size_t)ncam)); CKR(alloc(&Rt2, kCamTile * (size_t)ncam));
-  CKR(alloc(&obs_cam, (size_t)nobs)); CKR(alloc(&obs_lm, (size_t)nobs)); CKR(alloc(&obs_uv, 2 * (size_t)nobs));
+  CKR(alloc(&obs_cam, (size_t)nobs + 8));   // +8: bulk copies round up to 16 B
+  CKR(alloc(&obs_lm, (size_t)nobs)); CKR(alloc(&obs_uv, 2 * (size_t)nobs));
   CKR(alloc(&lm_ptr, (size_t)nlm + 1)); CKR(alloc(&lm_deg, (size_t)nlm));
   CKR(alloc(&cam_ptr, (size_t)ncam + 1)); CKR(alloc(&cam_deg, (size_t)ncam));
   CKR(alloc(&cam_perm, (size_t)nobs)); CKR(alloc(&cobs_lm, (size_t)nobs)); CKR(alloc(&cobs_uv, 2 * (size_t)nobs));
@@ -228,13 +277,14 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CKR(alloc(&yc, 6 * (size_t)ncam)); CKR(alloc(&yl, 3 * (size_t)nlm));
   CKR(alloc(&partial, (size_t)max_grid * 8)); CKR(alloc(&counter, 1)); CKR(alloc(&scal, SC_COUNT));
   CKR(alloc(&dev_info, 2)); CKR(alloc(&dup_flag, 1));   // dev_info[1]: potrs' own status (it would overwrite potrf's)
-  CK(cudaMallocHost(&scal_host, SC_COUNT * sizeof(double)));
-  CK(cudaMallocHost(&info_host, sizeof(int)));
+  CK(cudaMallocHost(&scal_host, (SC_COUNT + 2) * sizeof(double)));   // pinned mirror: scalars + potrf info
+  info_host = reinterpret_cast<int*>(scal_host + SC_COUNT);
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
   CK(cudaMemsetAsync(scal, 0, SC_COUNT * sizeof(double), stream));
   CK(cudaMemsetAsync(dup_flag, 0, sizeof(int), stream));
   CK(cudaMemsetAsync(yc, 0, 6 * (size_t)std::max(ncam, 1) * sizeof(double), stream));
 
+  tr.mark("cudaMalloc");
   CK(cudaMemcpyAsync(obs_cam, h_oc, nobs * sizeof(int), cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(obs_lm, h_ol, nobs * sizeof(int), cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(obs_uv, h_uv, 2 * nobs * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -243,6 +293,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   if (has_lm_const) CK(cudaMemcpyAsync(lm_const, h_lc, nlm, cudaMemcpyHostToDevice, stream));
   CKR(set_state(h_q, h_t, h_lm));
 
+  tr.mark("H2D");
   // ---- integer preprocessing on the device (bit-exact contract) ----
   CK(cudaMemsetAsync(lm_deg, 0, std::max(nlm, 1) * sizeof(int), stream));
   CK(cudaMemsetAsync(cam_deg, 0, std::max(ncam, 1) * sizeof(int), stream));
@@ -288,13 +339,16 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
     CK(cudaMemcpyAsync(cam_chunk_ptr, ccp.data(), ((size_t)ncam + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaStreamSynchronize(stream));
   }
+  tr.mark("index + chunks");
   CKR(build_pairs());
+  tr.mark("pair structure");
 
   // ---- Schur / dense workspaces ----
   CKR(alloc(&E, 18 * (size_t)nobs));
   CKR(alloc(&S, (size_t)ld * n)); CKR(alloc(&rhs, (size_t)n));
   CK(cudaMemsetAsync(S, 0, std::max<size_t>((size_t)ld * n, 1) * sizeof(double), stream));
   CK(cudaStreamSynchronize(stream));
+  tr.mark("workspaces");
   return STBA_OK;
 }
 
@@ -349,14 +403,25 @@ int Engine::get_state(double* h_q, double* h_t, double* h_lm) {
   return STBA_OK;
 }
 
+// landmark-major pass (full blocks or cost only) through the TMA-staged kernel
+template <bool COST_ONLY>
+static void launch_lin_lm2(Engine* e, const double* Rt_, const double* lm4_, double* Hll_, double* gl_, double* out) {
+  const int n_chunks = (e->n_lm + kLinThreads - 1) / kLinThreads;
+  const int grid = std::max(1, std::min(n_chunks, e->sm_count));
+  if (e->n_cam <= kMaxSmemCams)
+    k_lin_lm2<COST_ONLY, true><<<grid, kLinThreads, kLinSmemBytes, e->stream>>>(e->n_lm, e->n_cam, e->lm_ptr, e->obs_cam, e->obs_uv, Rt_, lm4_,
+                                                                              Hll_, gl_, e->partial, e->counter, out);
+  else
+    k_lin_lm2<COST_ONLY, false><<<grid, kLinThreads, kLinSmemBytes, e->stream>>>(e->n_lm, e->n_cam, e->lm_ptr, e->obs_cam, e->obs_uv, Rt_, lm4_,
+                                                                               Hll_, gl_, e->partial, e->counter, out);
+  ++e->launches;
+}
+
 // residual + Jacobian + J^T J / J^T r blocks at the current x
 int Engine::linearize() {
   if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q, cam_t, Rt);
-  LAUNCH(this, (k_lin_lm<false>), grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, obs_uv, Rt, lm4, Hll, gl,
-         partial, counter, scal + SC_COST);
-  if (n_chunk)
-    LAUNCH(this, k_lin_cam, grid_for(n_chunk, kBlock / 32), kBlock, n_chunk, chunk_cam, chunk_beg, chunk_end,
-           cobs_lm, cobs_uv, Rt, lm4, chunk_acc);
+  launch_lin_lm2<false>(this, Rt, lm4, Hll, gl, scal + SC_COST);
+  if (n_chunk) LAUNCH(this, k_lin_cam2, n_chunk, 32, chunk_cam, chunk_beg, chunk_end, cobs_lm, cobs_uv, Rt, lm4, chunk_acc);
   if (n_cam)
     LAUNCH(this, k_lin_cam_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, cam_const, chunk_acc, Rt, Hcc, gc);
   CK(cudaGetLastError());
@@ -405,7 +470,7 @@ int Engine::build_reduced(double radius, const stba_options& opt) {
          opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dl2, Linv, hl, E);
   if (n_free) {
     if (n_chunk)
-      LAUNCH(this, k_schur_diag, grid_for(n_chunk, kBlock / 32), kBlock, n_chunk, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
+      LAUNCH(this, k_schur_diag, n_chunk, 32, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
     LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, S, ld, rhs,
            nranks > 1 ? 0 : 1);
     if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, S, ld);
@@ -428,12 +493,15 @@ int Engine::dense_solve(int backend) {
   CK(cudaMemsetAsync(dev_info, 0, sizeof(int), stream));
   if (n > 0) {
     if (backend == STBA_DENSE_CUSOLVER) {
-      if (!cusolver) {   // created on first use: loading cuSOLVER costs tens of milliseconds
-        if (cusolverDnCreate(&cusolver) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
+      if (!cusolver) {   // one handle per process and device, created on first use
+        DeviceCtx& d = g_dev[device];
+        if (!d.cusolver && cusolverDnCreate(&d.cusolver) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
+        cusolver = d.cusolver;
         CKS(cusolverDnSetStream(cusolver, stream));
         CKS(cusolverDnDpotrf_bufferSize(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, ld, &potrf_lwork));
         CKR(alloc(&potrf_work, (size_t)potrf_lwork));
       }
+      CKS(cusolverDnSetStream(cusolver, stream));
       CKS(cusolverDnDpotrf(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, ld, potrf_work, potrf_lwork, dev_info));
       CKS(cusolverDnDpotrs(cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, S, ld, rhs, n, dev_info + 1));
       launches += 2;
@@ -461,8 +529,7 @@ int Engine::step_from_solution() {
 
 int Engine::candidate_cost() {
   if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q2, cam_t2, Rt2);
-  LAUNCH(this, (k_lin_lm<true>), grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, obs_uv, Rt2, lm4_2, nullptr, nullptr,
-         partial, counter, scal + SC_CAND);
+  launch_lin_lm2<true>(this, Rt2, lm4_2, nullptr, nullptr, scal + SC_CAND);
   // landmark-side scalars are per-rank partial sums: SC_CAND, SC_MCC_L, SC_STEP2_L, SC_XN2_L are contiguous
   CKR(allreduce_sum(scal + SC_CAND, 4));
   CK(cudaGetLastError());
@@ -852,13 +919,11 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
     switch (phase) {
       case 0: CKR(e.linearize()); break;
       case 1:
-        LAUNCH(&e, (stba::k_lin_lm<false>), e.grid_for(e.n_lm, stba::kBlock), stba::kBlock, e.n_lm, e.lm_ptr, e.obs_cam, e.obs_uv,
-               e.Rt, e.lm4, e.Hll, e.gl, e.partial, e.counter, e.scal + stba::SC_COST);
+        stba::launch_lin_lm2<false>(&e, e.Rt, e.lm4, e.Hll, e.gl, e.scal + stba::SC_COST);
         break;
       case 2:
         if (e.n_chunk)
-          LAUNCH(&e, stba::k_lin_cam, e.grid_for(e.n_chunk, stba::kBlock / 32), stba::kBlock, e.n_chunk, e.chunk_cam, e.chunk_beg,
-                 e.chunk_end, e.cobs_lm, e.cobs_uv, e.Rt, e.lm4, e.chunk_acc);
+          LAUNCH(&e, stba::k_lin_cam2, e.n_chunk, 32, e.chunk_cam, e.chunk_beg, e.chunk_end, e.cobs_lm, e.cobs_uv, e.Rt, e.lm4, e.chunk_acc);
         LAUNCH(&e, stba::k_lin_cam_finish, (e.n_cam + 127) / 128, 128, e.n_cam, e.cam_chunk_ptr, e.cam_const, e.chunk_acc, e.Rt, e.Hcc, e.gc);
         break;
       case 3: CKR(e.build_reduced(1e4, o)); break;

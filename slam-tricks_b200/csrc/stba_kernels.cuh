@@ -27,140 +27,19 @@ __global__ void k_cam_prep(int n_cam, const double* __restrict__ q, const double
   Rt[kCamTile * c + 9] = t[3 * c];
   Rt[kCamTile * c + 10] = t[3 * c + 1];
   Rt[kCamTile * c + 11] = t[3 * c + 2];
+  Rt[kCamTile * c + 12] = 0.0;
+  Rt[kCamTile * c + 13] = 0.0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// lin_lm — landmark-major pass: one thread per landmark walks its (contiguous) observations,
-// keeps H_ll (6 unique) and g_l (3) in registers and writes them once.  COST_ONLY evaluates
-// just 1/2 |r|^2 (the candidate-point cost of the trust-region loop).
-// ---------------------------------------------------------------------------------------------
-template <bool COST_ONLY>
-__global__ void __launch_bounds__(kBlock)
-k_lin_lm(int n_lm, const int* __restrict__ lm_ptr, const int* __restrict__ obs_cam,
-         const double* __restrict__ obs_uv, const double* __restrict__ Rt,
-         const double* __restrict__ lm4, double* __restrict__ Hll, double* __restrict__ gl,
-         double* partial, unsigned int* counter, double* out_cost) {
-  double cost[1] = {0.0};
-  for (int l = blockIdx.x * kBlock + threadIdx.x; l < n_lm; l += gridDim.x * kBlock) {
-    const double2 pxy = ldg2(lm4 + 4 * (size_t)l);
-    const double pz = __ldg(lm4 + 4 * (size_t)l + 2);
-    const int beg = lm_ptr[l], end = lm_ptr[l + 1];
-    double h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0, g0 = 0, g1 = 0, g2 = 0;
-    for (int o = beg; o < end; ++o) {
-      const int c = __ldg(obs_cam + o);
-      const double2 uv = ldg2(obs_uv + 2 * (size_t)o);
-      double T[kCamTile];
-      const double* tile = Rt + (size_t)kCamTile * c;
-#pragma unroll
-      for (int k = 0; k < kCamTile; k += 2) {
-        const double2 x = ldg2(tile + k);
-        T[k] = x.x;
-        T[k + 1] = x.y;
-      }
-      const Obs ob = project(T, pxy.x, pxy.y, pz, uv.x, uv.y);
-      cost[0] = fma(ob.r0, ob.r0, fma(ob.r1, ob.r1, cost[0]));
-      if (!COST_ONLY) {
-        double J0[3], J1[3];
-        landmark_jacobian(T, ob, J0, J1);
-        h0 = fma(J0[0], J0[0], fma(J1[0], J1[0], h0));
-        h1 = fma(J0[0], J0[1], fma(J1[0], J1[1], h1));
-        h2 = fma(J0[0], J0[2], fma(J1[0], J1[2], h2));
-        h3 = fma(J0[1], J0[1], fma(J1[1], J1[1], h3));
-        h4 = fma(J0[1], J0[2], fma(J1[1], J1[2], h4));
-        h5 = fma(J0[2], J0[2], fma(J1[2], J1[2], h5));
-        g0 = fma(J0[0], ob.r0, fma(J1[0], ob.r1, g0));
-        g1 = fma(J0[1], ob.r0, fma(J1[1], ob.r1, g1));
-        g2 = fma(J0[2], ob.r0, fma(J1[2], ob.r1, g2));
-      }
-    }
-    if (!COST_ONLY) {
-      double2* H = reinterpret_cast<double2*>(Hll + 6 * (size_t)l);
-      H[0] = make_double2(h0, h1);
-      H[1] = make_double2(h2, h3);
-      H[2] = make_double2(h4, h5);
-      gl[3 * (size_t)l] = g0;
-      gl[3 * (size_t)l + 1] = g1;
-      gl[3 * (size_t)l + 2] = g2;
-    }
-  }
-  cost[0] *= 0.5;
-  grid_reduce<1, kBlock>(cost, 1, partial, counter, out_cost);
-}
-
-// ---------------------------------------------------------------------------------------------
-// lin_cam — camera-major pass.  One warp per chunk of one camera's observations; everything is
-// accumulated in the CAMERA frame, where the per-observation blocks collapse to 23 sums
+// The linearisation kernels (lin_lm2 / lin_cam2) live in stba_lin.cuh.  lin_cam2 accumulates in
+// the CAMERA frame, where the per-observation blocks collapse to 23 sums
 //   T  (6)  = sum J_th^T J_th                       (theta-theta block, already body-frame)
 //   K  (7)  = sum J_th^T Pi'   : iz*a, iz*c, iz*b, iz*(a u + c v), iz*(b u + a v), iz*v, iz*u
 //   Q  (4)  = sum Pi'^T Pi'    : iz^2, iz^2 u, iz^2 v, iz^2 (u^2+v^2)
 //   gth(3)  = sum J_th^T r
 //   m  (3)  = sum Pi'^T r      : iz r0, iz r1, -iz (u r0 + v r1)
-// with a = uv, b = 1+u^2, c = 1+v^2.  The finish kernel rotates them into the world-frame
+// with a = uv, b = 1+u^2, c = 1+v^2.  The finish kernel below rotates them into the world-frame
 // translation tangent once per camera:  H_tt = R Q R^T, H_th,t = -K R^T, g_t = -R m.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock)
-k_lin_cam(int n_chunk, const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg,
-          const int* __restrict__ chunk_end, const int* __restrict__ cobs_lm,
-          const double* __restrict__ cobs_uv, const double* __restrict__ Rt,
-          const double* __restrict__ lm4, double* __restrict__ chunk_acc) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_grid = gridDim.x * (kBlock / 32);
-  for (int ch = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); ch < n_chunk; ch += warps_per_grid) {
-    const int c = chunk_cam[ch];
-    double T[kCamTile];
-#pragma unroll
-    for (int k = 0; k < kCamTile; ++k) T[k] = __ldg(Rt + (size_t)kCamTile * c + k);
-    double acc[kCamAcc];
-#pragma unroll
-    for (int k = 0; k < kCamAcc; ++k) acc[k] = 0.0;
-    const int end = chunk_end[ch];
-    for (int o = chunk_beg[ch] + lane; o < end; o += 32) {
-      const int l = __ldg(cobs_lm + o);
-      const double2 uv = ldg2(cobs_uv + 2 * (size_t)o);
-      const double2 pxy = ldg2(lm4 + 4 * (size_t)l);
-      const double pz = __ldg(lm4 + 4 * (size_t)l + 2);
-      const Obs ob = project(T, pxy.x, pxy.y, pz, uv.x, uv.y);
-      const double u = ob.u, v = ob.v, iz = ob.iz, r0 = ob.r0, r1 = ob.r1;
-      const double a = u * v, b = fma(u, u, 1.0), c2 = fma(v, v, 1.0);
-      // T (theta-theta): J_th = [[a,-b,v],[c,-a,-u]]
-      acc[0] = fma(a, a, fma(c2, c2, acc[0]));
-      acc[1] = fma(-a, b + c2, acc[1]);
-      acc[2] = fma(a, v, fma(-c2, u, acc[2]));
-      acc[3] = fma(b, b, fma(a, a, acc[3]));
-      acc[4] = fma(a, u, fma(-b, v, acc[4]));
-      acc[5] = fma(u, u, fma(v, v, acc[5]));
-      // K
-      const double aucv = fma(a, u, c2 * v), buav = fma(b, u, a * v);
-      acc[6] = fma(iz, a, acc[6]);
-      acc[7] = fma(iz, c2, acc[7]);
-      acc[8] = fma(iz, b, acc[8]);
-      acc[9] = fma(iz, aucv, acc[9]);
-      acc[10] = fma(iz, buav, acc[10]);
-      acc[11] = fma(iz, v, acc[11]);
-      acc[12] = fma(iz, u, acc[12]);
-      // Q
-      const double w = iz * iz;
-      acc[13] += w;
-      acc[14] = fma(w, u, acc[14]);
-      acc[15] = fma(w, v, acc[15]);
-      acc[16] = fma(w, b + c2 - 2.0, acc[16]);
-      // g_theta
-      acc[17] = fma(a, r0, fma(c2, r1, acc[17]));
-      acc[18] = fma(-b, r0, fma(-a, r1, acc[18]));
-      acc[19] = fma(v, r0, fma(-u, r1, acc[19]));
-      // m
-      const double s = fma(u, r0, v * r1);
-      acc[20] = fma(iz, r0, acc[20]);
-      acc[21] = fma(iz, r1, acc[21]);
-      acc[22] = fma(-iz, s, acc[22]);
-    }
-#pragma unroll
-    for (int k = 0; k < kCamAcc; ++k) {
-      const double r = warp_sum(acc[k]);
-      if (lane == 0) chunk_acc[(size_t)ch * kCamAcc + k] = r;
-    }
-  }
-}
 
 // one thread per camera: add the camera's chunk partials in chunk order, rotate, pack.
 __global__ void k_lin_cam_finish(int n_cam, const int* __restrict__ cam_chunk_ptr,
@@ -305,9 +184,9 @@ k_schur_lm(int n_lm, const int* __restrict__ lm_ptr, const int* __restrict__ obs
         continue;
       }
       const double2 uv = ldg2(obs_uv + 2 * (size_t)o);
-      double T[kCamTile];
+      double T[kCamVals];
 #pragma unroll
-      for (int k = 0; k < kCamTile; k += 2) {
+      for (int k = 0; k < kCamVals; k += 2) {
         const double2 x = ldg2(Rt + (size_t)kCamTile * c + k);
         T[k] = x.x; T[k + 1] = x.y;
       }
@@ -343,44 +222,42 @@ __global__ void k_cam_diag(int n_cam, const double* __restrict__ Hcc, const doub
   Dc2[i] = lm_diag(Hcc[(size_t)c * 21 + tri6(k, k)], sc[i], lo, hi, inv_radius);
 }
 
-// schur_diag — camera-major: per chunk  sum_a E_a E_a^T (21 unique) and sum_a E_a h_l(a) (6)
-__global__ void __launch_bounds__(kBlock)
-k_schur_diag(int n_chunk, const int* __restrict__ chunk_beg, const int* __restrict__ chunk_end,
+// schur_diag — camera-major: per chunk  sum_a E_a E_a^T (21 unique) and sum_a E_a h_l(a) (6).
+// One warp per CTA (grid = n_chunk): provably convergent, so the final reduction is plain SHFL.BFLY.
+__global__ void __launch_bounds__(32)
+k_schur_diag(const int* __restrict__ chunk_beg, const int* __restrict__ chunk_end,
              const int* __restrict__ cam_perm, const int* __restrict__ cobs_lm,
              const double* __restrict__ E, const double* __restrict__ hl,
              double* __restrict__ chunk_acc) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_grid = gridDim.x * (kBlock / 32);
-  for (int ch = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); ch < n_chunk; ch += warps_per_grid) {
-    double acc[kDiagAcc];
+  const int lane = threadIdx.x, ch = blockIdx.x;
+  double acc[kDiagAcc];
 #pragma unroll
-    for (int k = 0; k < kDiagAcc; ++k) acc[k] = 0.0;
-    const int end = chunk_end[ch];
-    for (int o = chunk_beg[ch] + lane; o < end; o += 32) {
-      const int a = __ldg(cam_perm + o);
-      const int l = __ldg(cobs_lm + o);
-      double e[18];
+  for (int k = 0; k < kDiagAcc; ++k) acc[k] = 0.0;
+  const int end = chunk_end[ch];
+  for (int o = chunk_beg[ch] + lane; o < end; o += 32) {
+    const int a = __ldg(cam_perm + o);
+    const int l = __ldg(cobs_lm + o);
+    double e[18];
 #pragma unroll
-      for (int k = 0; k < 18; k += 2) {
-        const double2 x = ldg2(E + 18 * (size_t)a + k);
-        e[k] = x.x; e[k + 1] = x.y;
-      }
-      const double h0 = __ldg(hl + 3 * (size_t)l), h1 = __ldg(hl + 3 * (size_t)l + 1), h2 = __ldg(hl + 3 * (size_t)l + 2);
-      int t = 0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = i; j < 6; ++j, ++t)
-          acc[t] = fma(e[3 * i], e[3 * j], fma(e[3 * i + 1], e[3 * j + 1], fma(e[3 * i + 2], e[3 * j + 2], acc[t])));
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-        acc[21 + i] = fma(e[3 * i], h0, fma(e[3 * i + 1], h1, fma(e[3 * i + 2], h2, acc[21 + i])));
+    for (int k = 0; k < 18; k += 2) {
+      const double2 x = ldg2(E + 18 * (size_t)a + k);
+      e[k] = x.x; e[k + 1] = x.y;
     }
+    const double h0 = __ldg(hl + 3 * (size_t)l), h1 = __ldg(hl + 3 * (size_t)l + 1), h2 = __ldg(hl + 3 * (size_t)l + 2);
+    int t = 0;
 #pragma unroll
-    for (int k = 0; k < kDiagAcc; ++k) {
-      const double r = warp_sum(acc[k]);
-      if (lane == 0) chunk_acc[(size_t)ch * kDiagAcc + k] = r;
-    }
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j, ++t)
+        acc[t] = fma(e[3 * i], e[3 * j], fma(e[3 * i + 1], e[3 * j + 1], fma(e[3 * i + 2], e[3 * j + 2], acc[t])));
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      acc[21 + i] = fma(e[3 * i], h0, fma(e[3 * i + 1], h1, fma(e[3 * i + 2], h2, acc[21 + i])));
+  }
+#pragma unroll
+  for (int k = 0; k < kDiagAcc; ++k) {
+    const double r = warp_sum(acc[k]);
+    if (lane == 0) chunk_acc[(size_t)ch * kDiagAcc + k] = r;
   }
 }
 
