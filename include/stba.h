@@ -151,6 +151,14 @@ int stba_ba_create(stba_ba** out, int device, int32_t n_cam, int32_t n_lm, int64
                    const double* cam_q, const double* cam_t, const double* lm,
                    const int32_t* obs_cam, const int32_t* obs_lm, const double* obs_uv,
                    const uint8_t* cam_const, const uint8_t* lm_const);
+/* flags: STBA_CREATE_LINEARIZE_ONLY builds only what stba_ba_linearize needs (no Schur pair
+ * structure, no E / S workspaces) — for streaming-size linearisation benchmarks whose reduced
+ * system would not fit (10k+ cameras). */
+#define STBA_CREATE_LINEARIZE_ONLY 1u
+int stba_ba_create_ex(stba_ba** out, int device, int32_t n_cam, int32_t n_lm, int64_t n_obs,
+                      const double* cam_q, const double* cam_t, const double* lm,
+                      const int32_t* obs_cam, const int32_t* obs_lm, const double* obs_uv,
+                      const uint8_t* cam_const, const uint8_t* lm_const, uint32_t flags);
 void stba_ba_destroy(stba_ba* ba);
 
 int stba_ba_set_state(stba_ba* ba, const double* cam_q, const double* cam_t, const double* lm);

@@ -18,6 +18,7 @@ SOLVER_CONTINUE, SOLVER_ABORT, SOLVER_TERMINATE_SUCCESSFULLY = 0, 1, 2
 DENSE_QR, SPARSE_SCHUR = 0, 1
 MANIFOLD_EUCLIDEAN, MANIFOLD_SO3_QUAT, MANIFOLD_SO3_LOG = 0, 1, 2
 DENSE_OWN, DENSE_CUSOLVER = 0, 1
+CREATE_LINEARIZE_ONLY = 1
 UNIQUE_ID_BYTES = 128
 
 
@@ -92,6 +93,8 @@ SIGNATURES = {
     "stba_device_count": (C.c_int, []),
     "stba_ba_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp,
                                  _ip, _ip, _dp, _bp, _bp]),
+    "stba_ba_create_ex": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp,
+                                    _ip, _ip, _dp, _bp, _bp, C.c_uint32]),
     "stba_ba_destroy": (None, [C.c_void_p]),
     "stba_ba_set_state": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "stba_ba_get_state": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),

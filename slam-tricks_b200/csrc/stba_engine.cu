@@ -91,6 +91,7 @@ struct Engine {
   int n_chunk = 0, chunk_size = 0, sm_count = 148, max_grid = 148 * 16;
   int64_t launches = 0;
   bool has_lm_const = false;
+  bool linearize_only = false;   // STBA_CREATE_LINEARIZE_ONLY: no Schur / dense workspaces
 
   double *cam_q = nullptr, *cam_t = nullptr, *lm4 = nullptr;
   double *cam_q2 = nullptr, *cam_t2 = nullptr, *lm4_2 = nullptr;
@@ -103,6 +104,7 @@ struct Engine {
   uint8_t *cam_const = nullptr, *lm_const = nullptr;
   int* free_of = nullptr;
   int *chunk_cam = nullptr, *chunk_beg = nullptr, *chunk_end = nullptr, *cam_chunk_ptr = nullptr;
+  unsigned int* cam_ticket = nullptr;   // per-camera arrival counters of lin_cam2 (self re-arming)
   int64_t* blk_ptr = nullptr;
   uint64_t* inc = nullptr;
   int* dup_flag = nullptr;
@@ -317,8 +319,9 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CK(cudaMemcpyAsync(h_cam_ptr.data(), cam_ptr, ((size_t)ncam + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   {
-    // aim for >= 16 warps per SM, chunks between 64 and 2048 observations (multiple of 32)
-    int64_t target = nobs / ((int64_t)sm_count * 16) + 1;
+    // aim for ~48 one-warp CTAs per SM (several waves at the register-limited occupancy), chunks
+    // between 64 and 2048 observations (multiple of 32)
+    int64_t target = nobs / ((int64_t)sm_count * 48) + 1;
     chunk_size = (int)std::min<int64_t>(2048, std::max<int64_t>(64, (target + 31) / 32 * 32));
     std::vector<int> cc, cb, ce, ccp((size_t)ncam + 1, 0);
     for (int c = 0; c < ncam; ++c) {
@@ -332,6 +335,10 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
     n_chunk = (int)cc.size();
     CKR(alloc(&chunk_cam, (size_t)n_chunk)); CKR(alloc(&chunk_beg, (size_t)n_chunk)); CKR(alloc(&chunk_end, (size_t)n_chunk));
     CKR(alloc(&cam_chunk_ptr, (size_t)ncam + 1));
+    CKR(alloc(&cam_ticket, (size_t)ncam));
+    CK(cudaMemsetAsync(cam_ticket, 0, std::max(ncam, 1) * sizeof(unsigned int), stream));
+    CK(cudaMemsetAsync(Hcc, 0, 21 * (size_t)std::max(ncam, 1) * sizeof(double), stream));   // constant / unobserved cameras stay zero
+    CK(cudaMemsetAsync(gc, 0, 6 * (size_t)std::max(ncam, 1) * sizeof(double), stream));
     CKR(alloc(&chunk_acc, (size_t)n_chunk * kDiagAcc));
     CK(cudaMemcpyAsync(chunk_cam, cc.data(), n_chunk * sizeof(int), cudaMemcpyHostToDevice, stream));
     CK(cudaMemcpyAsync(chunk_beg, cb.data(), n_chunk * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -340,13 +347,15 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
     CK(cudaStreamSynchronize(stream));
   }
   tr.mark("index + chunks");
-  CKR(build_pairs());
+  if (!linearize_only) CKR(build_pairs());
   tr.mark("pair structure");
 
   // ---- Schur / dense workspaces ----
-  CKR(alloc(&E, 18 * (size_t)nobs));
-  CKR(alloc(&S, (size_t)ld * n)); CKR(alloc(&rhs, (size_t)n));
-  CK(cudaMemsetAsync(S, 0, std::max<size_t>((size_t)ld * n, 1) * sizeof(double), stream));
+  if (!linearize_only) {
+    CKR(alloc(&E, 18 * (size_t)nobs));
+    CKR(alloc(&S, (size_t)ld * n)); CKR(alloc(&rhs, (size_t)n));
+    CK(cudaMemsetAsync(S, 0, std::max<size_t>((size_t)ld * n, 1) * sizeof(double), stream));
+  }
   CK(cudaStreamSynchronize(stream));
   tr.mark("workspaces");
   return STBA_OK;
@@ -406,7 +415,7 @@ int Engine::get_state(double* h_q, double* h_t, double* h_lm) {
 // landmark-major pass (full blocks or cost only) through the TMA-staged kernel
 template <bool COST_ONLY>
 static void launch_lin_lm2(Engine* e, const double* Rt_, const double* lm4_, double* Hll_, double* gl_, double* out) {
-  const int n_chunks = (e->n_lm + kLinThreads - 1) / kLinThreads;
+  const int n_chunks = (e->n_lm + kLinLm - 1) / kLinLm;
   const int grid = std::max(1, std::min(n_chunks, e->sm_count));
   if (e->n_cam <= kMaxSmemCams)
     k_lin_lm2<COST_ONLY, true><<<grid, kLinThreads, kLinSmemBytes, e->stream>>>(e->n_lm, e->n_cam, e->lm_ptr, e->obs_cam, e->obs_uv, Rt_, lm4_,
@@ -420,10 +429,17 @@ static void launch_lin_lm2(Engine* e, const double* Rt_, const double* lm4_, dou
 // residual + Jacobian + J^T J / J^T r blocks at the current x
 int Engine::linearize() {
   if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q, cam_t, Rt);
+  // (Running the two passes concurrently on two streams was measured and does not pay: lin_lm2 owns
+  // a whole SM's shared memory and 2/3 of its registers, so lin_cam2 only gets ~4 warps/SM beside it;
+  // 61.8 us vs 62.3 us at C and 472 us vs 373 us at 10x — profiles/r1_linearise_notes.md.)
+  if (nranks > 1 && n_cam) {   // cameras without local observations must not keep last iteration's reduced sums
+    CK(cudaMemsetAsync(Hcc, 0, 21 * (size_t)n_cam * sizeof(double), stream));
+    CK(cudaMemsetAsync(gc, 0, 6 * (size_t)n_cam * sizeof(double), stream));
+  }
   launch_lin_lm2<false>(this, Rt, lm4, Hll, gl, scal + SC_COST);
-  if (n_chunk) LAUNCH(this, k_lin_cam2, n_chunk, 32, chunk_cam, chunk_beg, chunk_end, cobs_lm, cobs_uv, Rt, lm4, chunk_acc);
-  if (n_cam)
-    LAUNCH(this, k_lin_cam_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, cam_const, chunk_acc, Rt, Hcc, gc);
+  if (n_chunk)
+    LAUNCH(this, k_lin_cam2, n_chunk, 32, chunk_cam, chunk_beg, chunk_end, cam_chunk_ptr, cobs_lm, cobs_uv, Rt, lm4, chunk_acc,
+           cam_ticket, Hcc, gc);
   CK(cudaGetLastError());
   linearized = true;
   reduced_built = false;
@@ -463,6 +479,7 @@ int Engine::post_linearize(const stba_options& opt, bool want_grad) {
 // S = H_cc + D_c^2 - sum E E^T (lower triangle, dense column-major), rhs = g_c - sum E h
 int Engine::build_reduced(double radius, const stba_options& opt) {
   if (!linearized) return STBA_ERR_INVALID_ARGUMENT;
+  if (linearize_only) return STBA_ERR_UNSUPPORTED;
   const double inv_r = 1.0 / radius;
   const uint8_t* lc = has_lm_const ? lm_const : nullptr;
   if (n_cam) LAUNCH(this, k_cam_diag, (6 * n_cam + 127) / 128, 128, n_cam, Hcc, sc, opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dc2);
@@ -549,6 +566,7 @@ int Engine::fetch_scalars() {
 // 128-byte scalar block per iteration; all state stays in HBM.
 // ------------------------------------------------------------------------------------------
 int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_callback cb, void* user) {
+  if (linearize_only) return STBA_ERR_UNSUPPORTED;
   CK(cudaSetDevice(device));
   using clk = std::chrono::steady_clock;
   const auto t_begin = clk::now();
@@ -767,10 +785,17 @@ int stba_device_count(void) {
 int stba_ba_create(stba_ba** out, int device, int32_t n_cam, int32_t n_lm, int64_t n_obs, const double* cam_q,
                    const double* cam_t, const double* lm, const int32_t* obs_cam, const int32_t* obs_lm,
                    const double* obs_uv, const uint8_t* cam_const, const uint8_t* lm_const) {
+  return stba_ba_create_ex(out, device, n_cam, n_lm, n_obs, cam_q, cam_t, lm, obs_cam, obs_lm, obs_uv, cam_const, lm_const, 0);
+}
+
+int stba_ba_create_ex(stba_ba** out, int device, int32_t n_cam, int32_t n_lm, int64_t n_obs, const double* cam_q,
+                      const double* cam_t, const double* lm, const int32_t* obs_cam, const int32_t* obs_lm,
+                      const double* obs_uv, const uint8_t* cam_const, const uint8_t* lm_const, uint32_t flags) {
   if (!out) return STBA_ERR_INVALID_ARGUMENT;
   *out = nullptr;
   stba_ba* h = new (std::nothrow) stba_ba();
   if (!h) return STBA_ERR_CUDA;
+  h->e.linearize_only = (flags & STBA_CREATE_LINEARIZE_ONLY) != 0;
   const int r = h->e.setup(device, n_cam, n_lm, n_obs, cam_q, cam_t, lm, obs_cam, obs_lm, obs_uv, cam_const, lm_const);
   if (r != STBA_OK) { delete h; return r; }
   int dup = 0;
@@ -840,6 +865,15 @@ int stba_ba_linearize(stba_ba* ba) {
   CK(cudaSetDevice(e.device));
   CKR(e.linearize());
   CK(cudaStreamSynchronize(e.stream));
+#ifdef STBA_LIN_TIMING
+  {
+    long long h[64];
+    cudaMemcpyFromSymbol(h, stba::g_lin_clk, sizeof(h));
+    fprintf(stderr, "[lin_lm2 clocks] init %lld camwait %lld |", h[1] - h[0], h[2] - h[1]);
+    for (int i = 0; i < 3; ++i) fprintf(stderr, " chunk%d: pre %lld wait %lld compute %lld tail %lld |", i, h[3 + 4 * i] - (i ? h[6 + 4 * (i - 1)] : h[2]), h[4 + 4 * i] - h[3 + 4 * i], h[5 + 4 * i] - h[4 + 4 * i], h[6 + 4 * i] - h[5 + 4 * i]);
+    fprintf(stderr, " reduce %lld total %lld\n", h[31] - h[30], h[31] - h[0]);
+  }
+#endif
   return STBA_OK;
 }
 
@@ -923,8 +957,8 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
         break;
       case 2:
         if (e.n_chunk)
-          LAUNCH(&e, stba::k_lin_cam2, e.n_chunk, 32, e.chunk_cam, e.chunk_beg, e.chunk_end, e.cobs_lm, e.cobs_uv, e.Rt, e.lm4, e.chunk_acc);
-        LAUNCH(&e, stba::k_lin_cam_finish, (e.n_cam + 127) / 128, 128, e.n_cam, e.cam_chunk_ptr, e.cam_const, e.chunk_acc, e.Rt, e.Hcc, e.gc);
+          LAUNCH(&e, stba::k_lin_cam2, e.n_chunk, 32, e.chunk_cam, e.chunk_beg, e.chunk_end, e.cam_chunk_ptr, e.cobs_lm, e.cobs_uv, e.Rt,
+                 e.lm4, e.chunk_acc, e.cam_ticket, e.Hcc, e.gc);
         break;
       case 3: CKR(e.build_reduced(1e4, o)); break;
       case 4: CKR(e.dense_solve(o.dense_backend)); break;

@@ -41,60 +41,6 @@ __global__ void k_cam_prep(int n_cam, const double* __restrict__ q, const double
 // with a = uv, b = 1+u^2, c = 1+v^2.  The finish kernel below rotates them into the world-frame
 // translation tangent once per camera:  H_tt = R Q R^T, H_th,t = -K R^T, g_t = -R m.
 
-// one thread per camera: add the camera's chunk partials in chunk order, rotate, pack.
-__global__ void k_lin_cam_finish(int n_cam, const int* __restrict__ cam_chunk_ptr,
-                                 const uint8_t* __restrict__ cam_const,
-                                 const double* __restrict__ chunk_acc, const double* __restrict__ Rt,
-                                 double* __restrict__ Hcc, double* __restrict__ gc) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cam) return;
-  double a[kCamAcc];
-#pragma unroll
-  for (int k = 0; k < kCamAcc; ++k) a[k] = 0.0;
-  if (!cam_const[c]) {
-    for (int ch = cam_chunk_ptr[c]; ch < cam_chunk_ptr[c + 1]; ++ch)
-#pragma unroll
-      for (int k = 0; k < kCamAcc; ++k) a[k] += chunk_acc[(size_t)ch * kCamAcc + k];
-  }
-  double R[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = Rt[(size_t)kCamTile * c + k];
-  double H[6][6];
-  // theta-theta
-  H[0][0] = a[0]; H[0][1] = a[1]; H[0][2] = a[2]; H[1][1] = a[3]; H[1][2] = a[4]; H[2][2] = a[5];
-  // K = sum J_th^T Pi'
-  const double K[3][3] = {{a[6], a[7], -a[9]}, {-a[8], -a[6], a[10]}, {a[11], -a[12], 0.0}};
-  // H_theta,t = -K R^T  -> [i][j] = -sum_k K[i][k] R[j][k]
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      H[i][3 + j] = -(K[i][0] * R[3 * j] + K[i][1] * R[3 * j + 1] + K[i][2] * R[3 * j + 2]);
-  // H_tt = R Q R^T
-  const double Q[3][3] = {{a[13], 0.0, -a[14]}, {0.0, a[13], -a[15]}, {-a[14], -a[15], a[16]}};
-  double RQ[3][3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      RQ[i][j] = R[3 * i] * Q[0][j] + R[3 * i + 1] * Q[1][j] + R[3 * i + 2] * Q[2][j];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = i; j < 3; ++j)
-      H[3 + i][3 + j] = RQ[i][0] * R[3 * j] + RQ[i][1] * R[3 * j + 1] + RQ[i][2] * R[3 * j + 2];
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = i; j < 6; ++j) Hcc[(size_t)c * 21 + tri6(i, j)] = H[i][j];
-  gc[(size_t)c * 6 + 0] = a[17];
-  gc[(size_t)c * 6 + 1] = a[18];
-  gc[(size_t)c * 6 + 2] = a[19];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    gc[(size_t)c * 6 + 3 + i] = -(R[3 * i] * a[20] + R[3 * i + 1] * a[21] + R[3 * i + 2] * a[22]);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Jacobi column scaling, computed once at x0 (Ceres: 1 / (1 + sqrt(squared column norm)))
 // ---------------------------------------------------------------------------------------------

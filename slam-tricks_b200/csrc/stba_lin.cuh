@@ -2,15 +2,15 @@
 // (per-observation reprojection residual + exact Jacobian + J^T J / J^T r block accumulation, J never
 // stored; algorithmic bytes 24 N_obs + 96 N_lm + 272 N_cam).
 //
-// lin_lm2 — landmark-major pass, persistent CTAs (one per SM):
+// lin_lm2 — landmark-major pass, persistent CTAs (one per SM, 512 threads):
 //   * the whole camera-tile table ([R|t], 112 B per camera) is staged ONCE per CTA into shared memory
 //     with a TMA bulk copy (cp.async.bulk, SASS UBLKCP) when it fits (n_cam <= kMaxSmemCams);
 //   * the observation stream (obs_cam i32 + obs_uv 2 x f64) of each chunk of 256 consecutive
 //     landmarks is contiguous; it is double-buffered into shared memory by TMA bulk copies signalled
 //     on mbarriers, issued one chunk ahead by thread 0;
-//   * one thread per landmark then walks its observations out of shared memory, keeps H_ll (6) and
-//     g_l (3) in registers and writes them once: no global-memory latency inside the loop, no
-//     atomics, no shuffles, deterministic.
+//   * two threads per landmark then walk alternate observations out of shared memory, keep their
+//     halves of H_ll (6) and g_l (3) in registers, combine them with one shuffle step and write
+//     once: no global-memory latency inside the loop, no atomics, deterministic.
 // lin_cam2 — camera-major pass, one warp per CTA per chunk of one camera's observations: four
 //   observations per lane in flight (index -> landmark gathers are the latency), camera-frame
 //   accumulation (23 sums, see stba_kernels.cuh), plain butterfly shuffles (a one-warp CTA is
@@ -20,11 +20,19 @@
 
 namespace stba {
 
-constexpr int kLinThreads = 256;       // landmarks per chunk == threads per CTA
+constexpr int kLinLm = 256;            // landmarks per chunk
+constexpr int kLinThreads = 512;       // two threads per landmark (alternate observations, combined by one shuffle step)
 constexpr int kStageObs = 2688;        // observation capacity of one stage (multiple of 4)
 constexpr int kMaxSmemCams = 1024;     // camera tiles that fit next to two stages
 constexpr int kStageBytes = kStageObs * 16 + kStageObs * 4;
 constexpr int kLinSmemBytes = 64 + 2 * kStageBytes + kMaxSmemCams * kCamTile * 8;   // barriers first
+
+#ifdef STBA_LIN_TIMING
+__device__ long long g_lin_clk[64];
+#define LTICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_lin_clk[i] = clock64(); } while (0)
+#else
+#define LTICK(i) do {} while (0)
+#endif
 
 template <bool COST_ONLY, bool CAM_SMEM>
 __global__ void __launch_bounds__(kLinThreads, 1)
@@ -38,7 +46,8 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
   double* s_cam_tiles = reinterpret_cast<double*>(smem_raw + 64 + 2 * kStageBytes);
   __shared__ int s_bounds[2][2];      // per stage: first staged observation (aligned down to 4), count or -1 (not staged)
   const int tid = threadIdx.x;
-  const int n_chunks = (n_lm + kLinThreads - 1) / kLinThreads;
+  const int n_chunks = (n_lm + kLinLm - 1) / kLinLm;
+  LTICK(0);
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -50,7 +59,7 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
 
   // producer: stage the observations of `chunk` into buffer `st`
   auto issue = [&](int chunk, int st) {
-    const int l0 = chunk * kLinThreads, l1 = min(l0 + kLinThreads, n_lm);
+    const int l0 = chunk * kLinLm, l1 = min(l0 + kLinLm, n_lm);
     const int o0 = lm_ptr[l0] & ~3, o1 = lm_ptr[l1];
     const int cnt = o1 - o0;
     if (cnt > kStageObs || cnt <= 0) {           // too many observations for a stage: read them from global
@@ -79,7 +88,9 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
     if ((int)blockIdx.x < n_chunks) issue(blockIdx.x, 0);
   }
   __syncthreads();
+  LTICK(1);
   if (CAM_SMEM) mbar_wait(&bars[2], 0);
+  LTICK(2);
 
   double cost[1] = {0.0};
   int it = 0;
@@ -90,20 +101,23 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
     // __syncthreads that ended the previous iteration)
     if (tid == 0 && chunk + (int)gridDim.x < n_chunks) issue(chunk + gridDim.x, st ^ 1);
     const int o_base = s_bounds[st][0], staged = s_bounds[st][1];
+    LTICK(3 + 4 * it);
     if (staged > 0) {
       mbar_wait(&bars[st], (st ? phase1 : phase0) & 1);
       if (st) ++phase1; else ++phase0;
     }
+    LTICK(4 + 4 * it);
     const double2* s_uv = reinterpret_cast<const double2*>(stage_base + st * kStageBytes);
     const int* s_oc = reinterpret_cast<const int*>(stage_base + st * kStageBytes + kStageObs * 16);
 
-    const int l = chunk * kLinThreads + tid;
+    // lanes 2i and 2i+1 share landmark l and take alternate observations
+    const int l = chunk * kLinLm + (tid >> 1), par = tid & 1;
+    double h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0, g0 = 0, g1 = 0, g2 = 0;
     if (l < n_lm) {
       const double2 pxy = ldg2(lm4 + 4 * (size_t)l);
       const double pz = __ldg(lm4 + 4 * (size_t)l + 2);
       const int beg = lm_ptr[l], end = lm_ptr[l + 1];
-      double h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0, g0 = 0, g1 = 0, g2 = 0;
-      for (int o = beg; o < end; ++o) {
+      for (int o = beg + par; o < end; o += 2) {
         int c;
         double2 uv;
         if (staged > 0) {
@@ -146,20 +160,35 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
           g2 = fma(J0[2], ob.r0, fma(J1[2], ob.r1, g2));
         }
       }
-      if (!COST_ONLY) {
-        double2* H = reinterpret_cast<double2*>(Hll + 6 * (size_t)l);
-        H[0] = make_double2(h0, h1);
-        H[1] = make_double2(h2, h3);
-        H[2] = make_double2(h4, h5);
-        gl[3 * (size_t)l] = g0;
-        gl[3 * (size_t)l + 1] = g1;
-        gl[3 * (size_t)l + 2] = g2;
+    }
+    LTICK(5 + 4 * it);
+    if (!COST_ONLY) {
+      // combine the two half sums (fixed order: even lane + odd lane); every lane of the CTA gets here
+      h0 += __shfl_xor_sync(0xffffffffu, h0, 1); h1 += __shfl_xor_sync(0xffffffffu, h1, 1);
+      h2 += __shfl_xor_sync(0xffffffffu, h2, 1); h3 += __shfl_xor_sync(0xffffffffu, h3, 1);
+      h4 += __shfl_xor_sync(0xffffffffu, h4, 1); h5 += __shfl_xor_sync(0xffffffffu, h5, 1);
+      g0 += __shfl_xor_sync(0xffffffffu, g0, 1); g1 += __shfl_xor_sync(0xffffffffu, g1, 1);
+      g2 += __shfl_xor_sync(0xffffffffu, g2, 1);
+      if (l < n_lm) {
+        if (par == 0) {
+          double2* H = reinterpret_cast<double2*>(Hll + 6 * (size_t)l);
+          H[0] = make_double2(h0, h1);
+          H[1] = make_double2(h2, h3);
+          H[2] = make_double2(h4, h5);
+        } else {
+          gl[3 * (size_t)l] = g0;
+          gl[3 * (size_t)l + 1] = g1;
+          gl[3 * (size_t)l + 2] = g2;
+        }
       }
     }
     __syncthreads();     // everyone is done with stage `st` and with s_bounds[st]
+    LTICK(6 + 4 * it);
   }
   cost[0] *= 0.5;
+  LTICK(30);
   grid_reduce<1, kLinThreads>(cost, 1, partial, counter, out_cost);
+  LTICK(31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -198,10 +227,50 @@ __device__ __forceinline__ void cam_accumulate(const double* __restrict__ T, dou
   acc[22] = fma(-iz, s, acc[22]);
 }
 
+// rotate the 23 camera-frame sums of one camera into the world-frame tangent and pack:
+// H_tt = R Q R^T, H_th,t = -K R^T, g_t = -R m  (one lane does it; ~200 flops per camera)
+__device__ __forceinline__ void cam_finish(const double* __restrict__ a, const double* __restrict__ R,
+                                           double* __restrict__ Hcc_c, double* __restrict__ gc_c) {
+  double H[6][6];
+  H[0][0] = a[0]; H[0][1] = a[1]; H[0][2] = a[2]; H[1][1] = a[3]; H[1][2] = a[4]; H[2][2] = a[5];
+  const double K[3][3] = {{a[6], a[7], -a[9]}, {-a[8], -a[6], a[10]}, {a[11], -a[12], 0.0}};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      H[i][3 + j] = -(K[i][0] * R[3 * j] + K[i][1] * R[3 * j + 1] + K[i][2] * R[3 * j + 2]);
+  const double Q[3][3] = {{a[13], 0.0, -a[14]}, {0.0, a[13], -a[15]}, {-a[14], -a[15], a[16]}};
+  double RQ[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      RQ[i][j] = R[3 * i] * Q[0][j] + R[3 * i + 1] * Q[1][j] + R[3 * i + 2] * Q[2][j];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j)
+      H[3 + i][3 + j] = RQ[i][0] * R[3 * j] + RQ[i][1] * R[3 * j + 1] + RQ[i][2] * R[3 * j + 2];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 6; ++j) Hcc_c[tri6(i, j)] = H[i][j];
+  gc_c[0] = a[17];
+  gc_c[1] = a[18];
+  gc_c[2] = a[19];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) gc_c[3 + i] = -(R[3 * i] * a[20] + R[3 * i + 1] * a[21] + R[3 * i + 2] * a[22]);
+}
+
+// The chunk of a camera that finishes LAST (per-camera ticket) adds that camera's chunk partials in
+// chunk order and writes H_cc / g_c: deterministic, no second launch.
 __global__ void __launch_bounds__(32)
 k_lin_cam2(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg, const int* __restrict__ chunk_end,
-           const int* __restrict__ cobs_lm, const double* __restrict__ cobs_uv, const double* __restrict__ Rt,
-           const double* __restrict__ lm4, double* __restrict__ chunk_acc) {
+           const int* __restrict__ cam_chunk_ptr, const int* __restrict__ cobs_lm, const double* __restrict__ cobs_uv,
+           const double* __restrict__ Rt, const double* __restrict__ lm4, double* __restrict__ chunk_acc,
+           unsigned int* __restrict__ cam_ticket, double* __restrict__ Hcc, double* __restrict__ gc) {
+  __shared__ double s_sum[kCamAcc];
+  __shared__ int s_last;
   const int ch = blockIdx.x, lane = threadIdx.x;
   const int c = chunk_cam[ch];
   double T[kCamVals];
@@ -242,6 +311,24 @@ k_lin_cam2(const int* __restrict__ chunk_cam, const int* __restrict__ chunk_beg,
     const double r = warp_sum(acc[k]);
     if (lane == 0) chunk_acc[(size_t)ch * kCamAcc + k] = r;
   }
+  // ---- per-camera ticket: the last chunk to arrive finishes the camera ----
+  const int ch0 = cam_chunk_ptr[c], ch1 = cam_chunk_ptr[c + 1];
+  if (lane == 0) {
+    __threadfence();
+    const unsigned int t = atomicInc(cam_ticket + c, (unsigned int)(ch1 - ch0 - 1));   // wraps to 0: re-armed
+    s_last = (t == (unsigned int)(ch1 - ch0 - 1));
+  }
+  __syncwarp();
+  if (!s_last) return;
+  __threadfence();
+  if (lane < kCamAcc) {
+    const volatile double* pa = chunk_acc;
+    double r = 0.0;
+    for (int k = ch0; k < ch1; ++k) r += pa[(size_t)k * kCamAcc + lane];
+    s_sum[lane] = r;
+  }
+  __syncwarp();
+  if (lane == 0) cam_finish(s_sum, T, Hcc + (size_t)c * 21, gc + (size_t)c * 6);
 }
 
 }  // namespace stba

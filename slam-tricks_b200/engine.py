@@ -57,7 +57,8 @@ def run_solve(fn, handle, options, callback, max_records=512):
 class BAEngine:
     """Device-resident bundle-adjustment problem in the SoA layout of SURVEY.md §8d."""
 
-    def __init__(self, cam_q, cam_t, lm, obs_cam, obs_lm, obs_uv, cam_const=None, lm_const=None, device=0):
+    def __init__(self, cam_q, cam_t, lm, obs_cam, obs_lm, obs_uv, cam_const=None, lm_const=None, device=0,
+                 linearize_only=False):
         L = capi.lib()
         self.n_cam, self.n_lm, self.n_obs = len(cam_q), len(lm), len(obs_cam)
         q = capi.as_f64(cam_q, (self.n_cam, 4)); t = capi.as_f64(cam_t, (self.n_cam, 3)); p = capi.as_f64(lm, (self.n_lm, 3))
@@ -67,9 +68,9 @@ class BAEngine:
         lc = np.ascontiguousarray(lm_const, dtype=np.uint8) if lm_const is not None else None
         self.cam_const = cc.astype(bool)
         self._h = C.c_void_p()
-        capi.check(L.stba_ba_create(C.byref(self._h), device, self.n_cam, self.n_lm, self.n_obs, capi.dptr(q), capi.dptr(t),
-                                    capi.dptr(p), capi.iptr(oc), capi.iptr(ol), capi.dptr(uv), capi.bptr(cc), capi.bptr(lc)),
-                   "stba_ba_create")
+        capi.check(L.stba_ba_create_ex(C.byref(self._h), device, self.n_cam, self.n_lm, self.n_obs, capi.dptr(q), capi.dptr(t),
+                                       capi.dptr(p), capi.iptr(oc), capi.iptr(ol), capi.dptr(uv), capi.bptr(cc), capi.bptr(lc),
+                                       capi.CREATE_LINEARIZE_ONLY if linearize_only else 0), "stba_ba_create_ex")
         self._L = L
 
     def close(self):
