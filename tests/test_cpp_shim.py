@@ -57,7 +57,9 @@ def test_ba_replay_matches_python_engine(stba, replay, tmp_path):
         s = e.solve()
         q2, t2, l2 = e.get_state()
     assert abs(final_cost - s.final_cost) <= 1e-12 * s.final_cost
-    assert np.array_equal(q, q2) and np.array_equal(t, t2) and np.array_equal(lm, l2)
+    # the pointer front door numbers cameras by first appearance, so sums run in a different order:
+    # equal to rounding, not bit for bit
+    assert np.max(np.abs(q - q2)) < 1e-9 and np.max(np.abs(t - t2)) < 1e-9 and np.max(np.abs(lm - l2)) < 1e-9
     assert "Iterations: %d" % len(s.iterations) in out.stdout
 
 
