@@ -221,6 +221,56 @@ int stba_comm_unique_id(char* id_out /* STBA_UNIQUE_ID_BYTES */);
 int stba_ba_comm_init(stba_ba* ba, int rank, int nranks, const char* id);
 
 /* ==================================================================================== */
+/* Front of the path: the two stages that feed the BA problem.    */
+/* ==================================================================================== */
+/* ProblemScene::CreateMeasurements, st20-g2o/src/src/sim_data.cpp:119-142: for every (camera,
+ * landmark) p_c = T_wc^-1 P; keep iff p_c.z >= 0, |x/z| < half_w, |y/z| < half_h (constants
+ * sim_data.h:211-212).  Outputs (any may be NULL): lm_deg i32[n_lm], cam_deg i32[n_cam]; the
+ * landmark -> [(camera, uv)] lists flattened landmark-major / camera-ascending into obs_cam,
+ * obs_lm i32[n_obs], obs_uv f64[n_obs,2] (rounded through float32 when round_uv_f32 != 0, as the
+ * reference's pcl::PointXY storage does, :135-136); the camera -> [landmark] lists flattened
+ * camera-major / landmark-ascending into cam_lm i32[n_obs].  *n_obs is always set; list outputs
+ * need capacity >= *n_obs (else STBA_ERR_OVERFLOW: call again with larger buffers).
+ * Index outputs are bit-exact (fixed evaluation order, no FMA contraction, ordered compaction). */
+int stba_visibility(int device, int32_t n_cam, int32_t n_lm, const double* cam_q, const double* cam_t,
+                    const double* pts, double half_w, double half_h, int32_t round_uv_f32,
+                    int64_t capacity, int64_t* n_obs, int32_t* lm_deg, int32_t* cam_deg,
+                    int32_t* obs_cam, int32_t* obs_lm, double* obs_uv, int32_t* cam_lm);
+
+/* The per-landmark solves of ProblemScene::Simulation, sim_data.cpp:298-311 (functor
+ * `Triangulation`, sim_data.h:165-194: residual uv - (R_cw P + t_cw).xy/z, cameras fixed), all
+ * landmarks in one kernel; each landmark runs its own Ceres-default trust-region LM (`opt`, NULL =
+ * defaults).  lm f64[n_lm,3] holds the initial points on entry and the result on exit;
+ * observations must be landmark-major.  Optional per-landmark outputs: iterations
+ * (= summary.iterations.size()), final_cost, termination (STBA_CONVERGENCE ...); kernel_ms =
+ * device time of the solve kernel. */
+int stba_triangulate(int device, int32_t n_cam, int32_t n_lm, int64_t n_obs, const double* cam_q,
+                     const double* cam_t, double* lm, const int32_t* obs_cam, const int32_t* obs_lm,
+                     const double* obs_uv, const stba_options* opt, int32_t* iterations,
+                     double* final_cost, int32_t* termination, float* kernel_ms);
+
+/* ==================================================================================== */
+/* Zhang calibration (BASELINE.json configs[3]).                   */
+/* Corners of all views are concatenated: view v owns [view_ptr[v], view_ptr[v+1]);        */
+/* obj_xy f64[n,2] board coordinates (Z = 0), img_uv f64[n,2] pixels.                      */
+/* ==================================================================================== */
+/* CalibSolver::computeHomoMats + reconstructIntriMat + reconstructExtriMat,
+ * st3-calibration/src/src/calib.cpp:49-173 (host: V small SVDs, as in the reference).
+ * intrinsics f64[4] = alpha, beta, u0, v0; poses f64[n_views,6] = se3.log() in Sophus order
+ * [rho, theta]; homographies f64[n_views,9] row-major (nullable). */
+int stba_calib_initialize(int32_t n_views, const int32_t* view_ptr, const double* obj_xy,
+                          const double* img_uv, double* intrinsics, double* poses,
+                          double* homographies);
+/* CalibSolver::totalOptimization, calib.cpp:282-422: joint Gauss-Newton over intrinsics (4),
+ * distortion k1 k2 k3 p1 p2 (5) and the V poses, on the device.  In/out: intrinsics, distortion,
+ * poses.  The reference runs max_iterations = 10 (:298) and stops at |update| < 1e-8 (:404).
+ * update_norms / costs (nullable) receive one value per iteration run. */
+int stba_calib_optimize(int device, int32_t n_views, const int32_t* view_ptr, const double* obj_xy,
+                        const double* img_uv, double* intrinsics, double* distortion, double* poses,
+                        int32_t max_iterations, double tolerance, int32_t* iterations_run,
+                        double* update_norms, double* costs, int64_t* gpu_launches);
+
+/* ==================================================================================== */
 /* Problem level: the ceres::Problem-shaped front door (pointer identity = block identity) */
 /* ==================================================================================== */
 typedef struct stba_problem stba_problem;

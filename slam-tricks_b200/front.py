@@ -1,0 +1,44 @@
+"""The two stages in front of the bundle-adjustment path, on the B200 (`stba_visibility`,
+`stba_triangulate`): `ProblemScene::CreateMeasurements` (st20-g2o/src/src/sim_data.cpp:119-142) and the
+per-landmark triangulation solves of `ProblemScene::Simulation` (sim_data.cpp:298-311)."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+HALF_W, HALF_H = 0.8, 0.6          # CAM_PLANE_HALF_WIDTH / HEIGHT, sim_data.h:211-212
+
+
+def visibility(cam_q, cam_t, pts, half_w=HALF_W, half_h=HALF_H, round_uv_f32=True, device=0):
+    """Returns dict(lm_deg, cam_deg, obs_cam, obs_lm, obs_uv, cam_lm): `_landmarkCameraVec` flattened
+    landmark-major / camera-ascending and `_cameraLandmarkVec` flattened camera-major / landmark-ascending."""
+    L = capi.lib()
+    n_cam, n_lm = len(cam_q), len(pts)
+    q = capi.as_f64(cam_q, (n_cam, 4)); t = capi.as_f64(cam_t, (n_cam, 3)); p = capi.as_f64(pts, (n_lm, 3))
+    n = C.c_int64(0)
+    lm_deg = np.zeros(n_lm, np.int32); cam_deg = np.zeros(n_cam, np.int32)
+    capi.check(L.stba_visibility(device, n_cam, n_lm, capi.dptr(q), capi.dptr(t), capi.dptr(p), half_w, half_h, int(round_uv_f32),
+                                 0, C.byref(n), capi.iptr(lm_deg), capi.iptr(cam_deg), None, None, None, None), "stba_visibility")
+    m = int(n.value)
+    oc = np.zeros(m, np.int32); ol = np.zeros(m, np.int32); uv = np.zeros((m, 2)); cl = np.zeros(m, np.int32)
+    if m:
+        capi.check(L.stba_visibility(device, n_cam, n_lm, capi.dptr(q), capi.dptr(t), capi.dptr(p), half_w, half_h, int(round_uv_f32),
+                                     m, C.byref(n), capi.iptr(lm_deg), capi.iptr(cam_deg), capi.iptr(oc), capi.iptr(ol), capi.dptr(uv),
+                                     capi.iptr(cl)), "stba_visibility")
+    return dict(lm_deg=lm_deg, cam_deg=cam_deg, obs_cam=oc, obs_lm=ol, obs_uv=uv, cam_lm=cl)
+
+
+def triangulate(cam_q, cam_t, lm0, obs_cam, obs_lm, obs_uv, options=None, device=0):
+    """Returns (lm [n,3], iterations i32[n], final_cost f64[n], termination list[str], kernel_ms)."""
+    L = capi.lib()
+    n_cam, n_lm, n_obs = len(cam_q), len(lm0), len(obs_cam)
+    q = capi.as_f64(cam_q, (n_cam, 4)); t = capi.as_f64(cam_t, (n_cam, 3))
+    lm = np.array(lm0, dtype=np.float64, order="C").reshape(n_lm, 3)
+    oc = np.ascontiguousarray(obs_cam, dtype=np.int32); ol = np.ascontiguousarray(obs_lm, dtype=np.int32)
+    uv = capi.as_f64(obs_uv, (n_obs, 2))
+    its = np.zeros(n_lm, np.int32); cost = np.zeros(n_lm); term = np.zeros(n_lm, np.int32); ms = C.c_float(0)
+    capi.check(L.stba_triangulate(device, n_cam, n_lm, n_obs, capi.dptr(q), capi.dptr(t), capi.dptr(lm), capi.iptr(oc), capi.iptr(ol),
+                                  capi.dptr(uv), C.byref(options) if options is not None else None, capi.iptr(its), capi.dptr(cost),
+                                  capi.iptr(term), C.byref(ms)), "stba_triangulate")
+    return lm, its, cost, [capi.TERMINATION[int(x)] for x in term], float(ms.value)
