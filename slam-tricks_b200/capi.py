@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstba.so")
+LIB_PATH = os.environ.get("STBA_LIB") or os.path.join(_HERE, "libstba.so")   # STBA_LIB: instrumented builds (profiling only)
 
 OK = 0
 ERR_NO_DEVICE = 3

@@ -323,6 +323,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
     // between 64 and 2048 observations (multiple of 32)
     int64_t target = nobs / ((int64_t)sm_count * 48) + 1;
     chunk_size = (int)std::min<int64_t>(2048, std::max<int64_t>(64, (target + 31) / 32 * 32));
+    if (const char* ov = getenv("STBA_CAM_CHUNK")) chunk_size = std::max(32, atoi(ov) / 32 * 32);   // tuning experiments only
     std::vector<int> cc, cb, ce, ccp((size_t)ncam + 1, 0);
     for (int c = 0; c < ncam; ++c) {
       ccp[c] = (int)cc.size();
