@@ -319,9 +319,11 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CK(cudaMemcpyAsync(h_cam_ptr.data(), cam_ptr, ((size_t)ncam + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   {
-    // aim for ~48 one-warp CTAs per SM (several waves at the register-limited occupancy), chunks
-    // between 64 and 2048 observations (multiple of 32)
-    int64_t target = nobs / ((int64_t)sm_count * 48) + 1;
+    // ~13 one-warp chunks per SM (about one round of the 16 resident warps), chunks between 64 and 2048
+    // observations (multiple of 32).  Measured at config C (tools/tune_cam_chunk.py): 160-observation
+    // chunks 33 us, 512 25 us, 1024 28 us — the per-chunk reduction + ticket are amortised over more
+    // observations while every SM still has a full set of warps.
+    int64_t target = nobs / ((int64_t)sm_count * 13) + 1;
     chunk_size = (int)std::min<int64_t>(2048, std::max<int64_t>(64, (target + 31) / 32 * 32));
     if (const char* ov = getenv("STBA_CAM_CHUNK")) chunk_size = std::max(32, atoi(ov) / 32 * 32);   // tuning experiments only
     std::vector<int> cc, cb, ce, ccp((size_t)ncam + 1, 0);
@@ -430,9 +432,11 @@ static void launch_lin_lm2(Engine* e, const double* Rt_, const double* lm4_, dou
 // residual + Jacobian + J^T J / J^T r blocks at the current x
 int Engine::linearize() {
   if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q, cam_t, Rt);
-  // (Running the two passes concurrently on two streams was measured and does not pay: lin_lm2 owns
-  // a whole SM's shared memory and 2/3 of its registers, so lin_cam2 only gets ~4 warps/SM beside it;
-  // 61.8 us vs 62.3 us at C and 472 us vs 373 us at 10x — profiles/r1_linearise_notes.md.)
+  // Two alternatives were measured and do not pay (profiles/r1_linearise_notes.md): the two passes on
+  // two streams (lin_lm2 owns a whole SM's shared memory and 2/3 of its registers: 61.8 vs 62.3 us),
+  // and one fused persistent launch of k_cam_prep + lin_lm2 + lin_cam2 (60.3 vs 53.5 us: the camera-major
+  // chunks then start only after the CTA's landmark chunks, and both passes are bound by the latency
+  // of their dependent cold loads, not by launch overhead).
   if (nranks > 1 && n_cam) {   // cameras without local observations must not keep last iteration's reduced sums
     CK(cudaMemsetAsync(Hcc, 0, 21 * (size_t)n_cam * sizeof(double), stream));
     CK(cudaMemsetAsync(gc, 0, 6 * (size_t)n_cam * sizeof(double), stream));

@@ -117,9 +117,10 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
       const double2 pxy = ldg2(lm4 + 4 * (size_t)l);
       const double pz = __ldg(lm4 + 4 * (size_t)l + 2);
       const int beg = lm_ptr[l], end = lm_ptr[l + 1];
-      for (int o = beg + par; o < end; o += 2) {
-        int c;
-        double2 uv;
+      // two observations per trip, as two independent chains (index -> tile -> projection -> 1/z ->
+      // Jacobian): with 16 warps per SM the latency of ONE such chain per thread left the FP64 pipe at
+      // 20 % (profiles/r1_lin_full.md); the second chain fills its bubbles.
+      auto fetch = [&](int o, int& c, double2& uv) {
         if (staged > 0) {
           c = s_oc[o - o_base];
           uv = s_uv[o - o_base];
@@ -127,7 +128,8 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
           c = __ldg(obs_cam + o);
           uv = ldg2(obs_uv + 2 * (size_t)o);
         }
-        double T[kCamVals];
+      };
+      auto tile_of = [&](int c, double* T) {
         if (CAM_SMEM) {
           const double2* tile = reinterpret_cast<const double2*>(s_cam_tiles + (size_t)kCamTile * c);
 #pragma unroll
@@ -144,7 +146,8 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
             T[k + 1] = x.y;
           }
         }
-        const Obs ob = project(T, pxy.x, pxy.y, pz, uv.x, uv.y);
+      };
+      auto accumulate = [&](const double* T, const Obs& ob) {
         cost[0] = fma(ob.r0, ob.r0, fma(ob.r1, ob.r1, cost[0]));
         if (!COST_ONLY) {
           double J0[3], J1[3];
@@ -159,6 +162,29 @@ k_lin_lm2(int n_lm, int n_cam, const int* __restrict__ lm_ptr, const int* __rest
           g1 = fma(J0[1], ob.r0, fma(J1[1], ob.r1, g1));
           g2 = fma(J0[2], ob.r0, fma(J1[2], ob.r1, g2));
         }
+      };
+      int o = beg + par;
+      for (; o + 2 < end; o += 4) {
+        int ca, cb;
+        double2 uva, uvb;
+        fetch(o, ca, uva);
+        fetch(o + 2, cb, uvb);
+        double Ta[kCamVals], Tb[kCamVals];
+        tile_of(ca, Ta);
+        tile_of(cb, Tb);
+        const Obs oa = project(Ta, pxy.x, pxy.y, pz, uva.x, uva.y);
+        const Obs ob = project(Tb, pxy.x, pxy.y, pz, uvb.x, uvb.y);
+        accumulate(Ta, oa);
+        accumulate(Tb, ob);
+      }
+      if (o < end) {
+        int c;
+        double2 uv;
+        fetch(o, c, uv);
+        double T[kCamVals];
+        tile_of(c, T);
+        const Obs ob = project(T, pxy.x, pxy.y, pz, uv.x, uv.y);
+        accumulate(T, ob);
       }
     }
     LTICK(5 + 4 * it);
