@@ -53,34 +53,43 @@ def load_scene(name):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled through
+    NVML every 10 ms (the timed region is ~0.2 s; nvidia-smi takes longer than that to start)."""
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.rows, self._halt, self.max_mhz = index, [], threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
+        nv = self.nv
+        if nv is None:
+            return
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(mhz), [n for n, b in bits.items() if r & b]))
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.01)
 
     def finish(self):
         self._halt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        self.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n in r[1]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.rows), "how": "NVML, 10 ms period, during the timed region"}
 
 
 def peaks():
@@ -88,6 +97,15 @@ def peaks():
     if os.path.exists(p):
         return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the contract kernels, from the committed
+    `ncu --set full` capture (profiles/lin_traffic.json, written by tools/ncu_summary.py traffic)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "lin_traffic.json")))
+    except Exception:
+        return None
 
 
 def algorithmic_bytes(n_cam, n_lm, n_obs):
@@ -240,7 +258,8 @@ def main():
         ab = algorithmic_bytes(n_cam, len(lm), len(oc))
         ach = ab / (ms.mean() * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_lin_lm+k_lin_cam(+finish)", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": how, "algorithmic_bytes": ab,
+                    "frac": ach / pk["hbm_gbs"], "traffic": (measured_traffic() or {}).get("bytes_per_linearisation") if args.workload == "C" else None,
+                    "traffic_source": (measured_traffic() or {}).get("source"), "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "algorithmic_bytes": ab,
                     "launch_ms": float(ms.mean()), "l2": "flushed between repetitions (192 MiB write sweep)"}
     if rank == 0 and world == 1 and args.scaled > 1:
         # the same kernels on `scaled` side-by-side copies of the workload: the observation stream no
@@ -270,6 +289,17 @@ def main():
                                    "launch_ms": float(dms.mean())}
         extra["roofline_dense"]["frac"] = extra["roofline_dense"]["achieved"] / fp64 if fp64 else None
         extra["phase_ms_isolated"] = {ph: float(eng.time_phase(ph, reps=5)[1:].mean()) for ph in ("lin_lm", "lin_cam", "schur", "dense_own", "dense_cusolver", "backsub", "cost")}
+    if rank == 0 and world == 1 and args.workload == "C":
+        # the rows either side of the path through their C-ABI calls with host buffers
+        t1 = time.perf_counter()
+        vis = stba.front.visibility(d["cam_q"], d["cam_t"], d["lm"])
+        t2 = time.perf_counter()
+        _, its, _, _, tri_ms = stba.front.triangulate(d["cam_q"], d["cam_t"], d["lm"], d["obs_cam"], d["obs_lm"], d["obs_uv"])
+        t3 = time.perf_counter()
+        extra["front"] = {"visibility": {"pairs_tested": n_cam * n_lm_total, "visible": int(len(vis["obs_cam"])), "e2e_ms": 1e3 * (t2 - t1),
+                                         "note": "stba_visibility: predicate + ordered compaction, host buffers in and out"},
+                          "triangulate": {"landmarks": n_lm_total, "observations": n_obs_total, "kernel_ms": tri_ms, "e2e_ms": 1e3 * (t3 - t2),
+                                          "mean_lm_iterations": float(its.mean())}}
     if rank == 0:
         extra["phase_ms_per_solve"] = {k: v for k, v in last.phase_ms.items()}
         extra["iterations_per_solve"] = n_iters(last)

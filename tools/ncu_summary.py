@@ -74,5 +74,26 @@ def full(path):
         print()
 
 
+def traffic(path):
+    """profiles/lin_traffic.json: DRAM bytes per launch of lin_lm2 + lin_cam2 (mean over the captured launches)."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for d in data:
+        k = short(d[idx["Kernel Name"]])
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(d[idx[m]].replace(",", "")) * scale[units[idx[m]]]
+        per.setdefault(k, []).append(tot)
+    kern = {k: sum(v) / len(v) for k, v in per.items()}
+    lin = sum(v for k, v in kern.items() if k.startswith("k_lin_lm2<0") or k.startswith("k_lin_cam2"))
+    print(json.dumps({"bytes_per_linearisation": lin, "per_kernel": kern, "source": "ncu --set full capture " + path.split("/")[-1] +
+                      " (dram__bytes_read.sum + dram__bytes_write.sum, mean per launch of k_lin_lm2 + k_lin_cam2)"}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
