@@ -238,17 +238,24 @@ def main():
         d2h = d["cam_q"].nbytes + d["cam_t"].nbytes + d["lm"].nbytes
         e2e_steps = max(2, min(args.steps, 5))
         te, ite = 0.0, 0
+        # the step's inputs live in PINNED host memory (the contract's e2e definition); outputs come back into fresh NumPy arrays
+        keep = {k: torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in ("cam_q", "cam_t", "lm", "obs_cam", "obs_lm", "obs_uv", "cam_const")}
+        hp = {k: v.numpy() for k, v in keep.items()}
+
+        def make_engine_pinned():
+            return stba.engine.BAEngine(hp["cam_q"], hp["cam_t"], hp["lm"], hp["obs_cam"], hp["obs_lm"], hp["obs_uv"], hp["cam_const"], device=local)
+
         for i in range(1 + e2e_steps):
             torch.cuda.synchronize()
             t1 = time.perf_counter()
-            with make_engine() as e2:
+            with make_engine_pinned() as e2:
                 s2 = e2.solve(opt)
                 e2.get_state()
             if i:
                 te += time.perf_counter() - t1; ite += n_iters(s2)
         e2e = {"value": ite / te, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": e2e_steps, "ms_per_step": 1e3 * te / e2e_steps,
-               "includes": "stba_ba_create (H2D + index preprocessing + pair structure) + stba_ba_solve + stba_ba_get_state"}
+               "includes": "stba_ba_create (H2D from pinned host memory + validation + index preprocessing + pair structure) + stba_ba_solve + stba_ba_get_state (D2H) + stba_ba_destroy"}
 
     # ---- roofline of the contract kernel (linearise = lin_lm + lin_cam), L2 flushed between reps ----
     roofline = None; extra = {}
@@ -258,7 +265,7 @@ def main():
         ab = algorithmic_bytes(n_cam, len(lm), len(oc))
         ach = ab / (ms.mean() * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_lin_lm+k_lin_cam(+finish)", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / pk["hbm_gbs"], "traffic": (measured_traffic() or {}).get("bytes_per_linearisation") if args.workload == "C" else None,
+                    "frac": ach / pk["hbm_gbs"], "traffic": (measured_traffic() or {}).get("bytes_per_linearisation") if (args.workload == "C" and world == 1) else None,
                     "traffic_source": (measured_traffic() or {}).get("source"), "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "algorithmic_bytes": ab,
                     "launch_ms": float(ms.mean()), "l2": "flushed between repetitions (192 MiB write sweep)"}
     if rank == 0 and world == 1 and args.scaled > 1:

@@ -271,6 +271,29 @@ int stba_calib_optimize(int device, int32_t n_views, const int32_t* view_ptr, co
                         double* update_norms, double* costs, int64_t* gpu_launches);
 
 /* ==================================================================================== */
+/* SE(3) pose graph (BASELINE.json configs[4]).  The reference has no      */
+/* pose-graph solver: inputs follow its pose-chain simulator and recorded tracks             */
+/* (st4-kalman/src/src/pose_simulation.cpp:17-88, st4-kalman/output/{truth,obs}.csv), the  */
+/* Jacobians its SE(3) notes (st23-lie-group-v2/doc.tex:862-997); oracle/pg_oracle.py is the */
+/* specification.  Poses q f64[n,4] xyzw + t f64[n,3] (body -> world); edge e = (ei < ej,    */
+/* measured T_i^-1 T_j as zq f64[m,4], zt f64[m,3]); residual Log(Z^-1 T_i^-1 T_j) in Sophus */
+/* order [rho, theta]; manifold T <- T Exp(delta); pose 0 constant.  J^T J is block-banded:  */
+/* max(ej - ei) <= 16 blocks is supported (STBA_ERR_UNSUPPORTED beyond).                    */
+/* ==================================================================================== */
+typedef struct stba_pg stba_pg;
+int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, const double* q,
+                   const double* t, const int32_t* ei, const int32_t* ej, const double* zq,
+                   const double* zt);
+void stba_pg_destroy(stba_pg* pg);
+int stba_pg_get_state(stba_pg* pg, double* q, double* t);
+/* one linearisation at the current state: cost = 1/2 |r|^2, gradient g f64[n,6], diagonal 6x6
+ * blocks of J^T J Hdiag f64[n,36] (row-major), half-bandwidth in blocks.  Any output may be NULL. */
+int stba_pg_linearize(stba_pg* pg, double* cost, double* g, double* Hdiag, int32_t* bandwidth);
+/* Ceres-faithful trust-region LM with an exact block-banded Cholesky solve per iteration */
+int stba_pg_solve(stba_pg* pg, const stba_options* opt, stba_summary* summary,
+                  stba_iteration_callback cb, void* user);
+
+/* ==================================================================================== */
 /* Problem level: the ceres::Problem-shaped front door (pointer identity = block identity) */
 /* ==================================================================================== */
 typedef struct stba_problem stba_problem;

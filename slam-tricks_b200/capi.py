@@ -119,6 +119,11 @@ SIGNATURES = {
                                    _ip, _dp, _ip, C.POINTER(C.c_float)]),
     "stba_calib_initialize": (C.c_int, [C.c_int32, _ip, _dp, _dp, _dp, _dp, _dp]),
     "stba_calib_optimize": (C.c_int, [C.c_int, C.c_int32, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int32, C.c_double, _ip, _dp, _dp, _lp]),
+    "stba_pg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int64, _dp, _dp, _ip, _ip, _dp, _dp]),
+    "stba_pg_destroy": (None, [C.c_void_p]),
+    "stba_pg_get_state": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "stba_pg_linearize": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _ip]),
+    "stba_pg_solve": (C.c_int, [C.c_void_p, C.POINTER(Options), C.POINTER(SummaryStruct), ITERATION_CALLBACK, C.c_void_p]),
     "stba_problem_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "stba_problem_destroy": (None, [C.c_void_p]),
     "stba_problem_add_parameter_block": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),

@@ -461,6 +461,17 @@ k_x_norm(int n_cam, int n_lm, const uint8_t* __restrict__ cam_const, const uint8
 // ---------------------------------------------------------------------------------------------
 // integer preprocessing (bit-exact contract)
 // ---------------------------------------------------------------------------------------------
+// index ranges + landmark-major order of the observation list (the contract of stba_ba_create)
+__global__ void k_validate_obs(int64_t n, const int* __restrict__ oc, const int* __restrict__ ol, int n_cam, int n_lm,
+                               int* __restrict__ bad) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = i; k < n; k += stride) {
+    const int c = oc[k], l = ol[k];
+    if (c < 0 || c >= n_cam || l < 0 || l >= n_lm || (k && ol[k - 1] > l)) *bad = 1;
+  }
+}
+
 __global__ void k_histogram(int64_t n, const int* __restrict__ key, int* __restrict__ hist) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     atomicAdd(hist + key[i], 1);
