@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="stba", choices=["stba", "reference"])
     ap.add_argument("--workload", default="C", choices=["B", "C"])
-    ap.add_argument("--dense", default="default", choices=["default", "own", "cusolver"])
+    ap.add_argument("--dense", default="default", choices=["default", "own", "cusolver", "hybrid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaled", type=int, default=10, help="copies of the workload for the streaming-size roofline (0/1 = skip)")
     args = ap.parse_args()
@@ -187,7 +187,7 @@ def main():
 
     opt = stba.capi.Options()
     if args.dense != "default":
-        opt.dense_backend = stba.capi.DENSE_OWN if args.dense == "own" else stba.capi.DENSE_CUSOLVER
+        opt.dense_backend = {"own": stba.capi.DENSE_OWN, "cusolver": stba.capi.DENSE_CUSOLVER, "hybrid": stba.capi.DENSE_HYBRID}[args.dense]
     eng = make_engine()
     if world > 1:
         ids = [stba.engine.comm_unique_id() if rank == 0 else None]
@@ -289,13 +289,14 @@ def main():
     if rank == 0 and world == 1:      # the remaining phases contain collectives when world > 1: single-GPU only
         fp64 = stba.engine.peak_fp64(local)
         n = 6 * int((d["cam_const"] == 0).sum())
-        dense_phase = "dense_own" if opt.dense_backend == stba.capi.DENSE_OWN else "dense_cusolver"
+        dense_name = {stba.capi.DENSE_OWN: "own", stba.capi.DENSE_CUSOLVER: "cusolver", stba.capi.DENSE_HYBRID: "hybrid"}[opt.dense_backend]
+        dense_phase = "dense_" + dense_name
         dms = eng.time_phase(dense_phase, reps=5)[1:]
         extra["roofline_dense"] = {"bound": "fp64", "kernel": "reduced-camera Cholesky + solve (n=%d)" % n, "achieved": (n ** 3 / 3 + 2 * n * n) / (dms.mean() * 1e-3) / 1e12,
                                    "peak": fp64, "unit": "TFLOP/s", "peak_source": "stba_peak_fp64 (DFMA chains, measured in this run)",
                                    "launch_ms": float(dms.mean())}
         extra["roofline_dense"]["frac"] = extra["roofline_dense"]["achieved"] / fp64 if fp64 else None
-        extra["phase_ms_isolated"] = {ph: float(eng.time_phase(ph, reps=5)[1:].mean()) for ph in ("lin_lm", "lin_cam", "schur", "dense_own", "dense_cusolver", "backsub", "cost")}
+        extra["phase_ms_isolated"] = {ph: float(eng.time_phase(ph, reps=5)[1:].mean()) for ph in ("lin_lm", "lin_cam", "schur", "dense_own", "dense_cusolver", "dense_hybrid", "backsub", "cost")}
     if rank == 0 and world == 1 and args.workload == "C":
         # the rows either side of the path through their C-ABI calls with host buffers
         t1 = time.perf_counter()
@@ -329,7 +330,8 @@ def main():
                            % (args.workload, n_cam, n_lm_total, n_obs_total),
                            "step": "one full LM solve from x0 (Ceres defaults, stops on its own tolerance tests)",
                            "parallelism": "landmark-sharded x%d, replicated reduced solve" % world if world > 1 else "single GPU",
-                           "dense_backend": "own" if opt.dense_backend == stba.capi.DENSE_OWN else "cusolver",
+                           "dense_backend": {stba.capi.DENSE_OWN: "own (hand-written DMMA Cholesky + substitutions)", stba.capi.DENSE_CUSOLVER: "cusolver (library potrf + potrs)",
+                                             stba.capi.DENSE_HYBRID: "hybrid (cusolverDnDpotrf + own one-launch forward/backward substitutions)"}[opt.dense_backend],
                            "l2": "working set (E 144 MB + S 287 MB) exceeds L2; inputs re-read every iteration"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "device_ms_per_step": dev_ms / args.steps}

@@ -69,6 +69,7 @@ extern "C" {
 /* ---- reduced-system (dense camera Cholesky) back end -------------------------------- */
 #define STBA_DENSE_OWN 0      /* hand-written blocked Cholesky (csrc/stba_chol.cu) */
 #define STBA_DENSE_CUSOLVER 1 /* cusolverDnDpotrf/Dpotrs — the library yard-stick */
+#define STBA_DENSE_HYBRID 2   /* cusolverDnDpotrf + the own one-launch forward/backward substitutions */
 
 typedef struct stba_options {
   /* Ceres 2.0/2.1 Solver::Options defaults; see stba_options_init */
@@ -79,7 +80,7 @@ typedef struct stba_options {
   int32_t update_state_every_iteration;    /* 0; test_ceres.h:138 sets it for the callback */
   int32_t minimizer_progress_to_stdout;    /* 0; solver.hpp:278 */
   int32_t num_threads;                     /* accepted and ignored (reference sets 1) */
-  int32_t dense_backend;                   /* STBA_DENSE_OWN */
+  int32_t dense_backend;                   /* STBA_DENSE_HYBRID */
   double initial_trust_region_radius;      /* 1e4 */
   double max_trust_region_radius;          /* 1e16 */
   double min_trust_region_radius;          /* 1e-32 */
@@ -201,7 +202,7 @@ int stba_ba_solve(stba_ba* ba, const stba_options* opt, stba_summary* summary,
 /* Timing helpers (CUDA events on the engine's own stream; warm-up is the caller's job).
  * phase: 0 = linearise (lin_lm + lin_cam), 1 = lin_lm only, 2 = lin_cam only, 3 = schur build,
  * 4 = dense factor+solve (default back end), 5 = back-substitution+update, 6 = candidate cost,
- * 7 = dense with STBA_DENSE_OWN, 8 = dense with STBA_DENSE_CUSOLVER.
+ * 7 = dense with STBA_DENSE_OWN, 8 = dense with STBA_DENSE_CUSOLVER, 9 = dense with STBA_DENSE_HYBRID.
  * Writes `reps` per-launch durations in milliseconds; flush_l2 != 0 rewrites a >L2 buffer
  * between repetitions (outside the timed region). */
 int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms);

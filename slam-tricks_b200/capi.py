@@ -17,7 +17,7 @@ TERMINATION = {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE", 3: "USER_SUC
 SOLVER_CONTINUE, SOLVER_ABORT, SOLVER_TERMINATE_SUCCESSFULLY = 0, 1, 2
 DENSE_QR, SPARSE_SCHUR = 0, 1
 MANIFOLD_EUCLIDEAN, MANIFOLD_SO3_QUAT, MANIFOLD_SO3_LOG = 0, 1, 2
-DENSE_OWN, DENSE_CUSOLVER = 0, 1
+DENSE_OWN, DENSE_CUSOLVER, DENSE_HYBRID = 0, 1, 2
 CREATE_LINEARIZE_ONLY = 1
 UNIQUE_ID_BYTES = 128
 

@@ -603,6 +603,165 @@ k_trsv_bwd_all(const double* __restrict__ S, int ld, int n, int T, const double*
   if (t == 0) st_release(flags + j, 1);
 }
 
+// ---- triangular solves on an existing factor (any potrf) ---------------------------------------
+// k_inv128: inverse of the 128 x 128 lower-triangular diagonal block k of a finished factor, one CTA
+// per block (all T blocks in parallel): four 32 x 32 inverses on four warps, then the off-diagonal
+// blocks exactly as k_inv_offdiag.
+__global__ void __launch_bounds__(PT, 1)
+k_inv128(const double* __restrict__ S, int ld, int n, double* __restrict__ LinvAll) {
+  extern __shared__ __align__(16) double sm[];
+  double* D = sm;
+  double* xd = sm + NB * PLD;
+  double* Tm = xd + NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k0 = (int)blockIdx.x * NB, nb = min(NB, n - k0);
+  double* Linv = LinvAll + (size_t)blockIdx.x * NB * NB;
+  for (int e = tid; e < NB * NB; e += PT) {
+    const int r = e % NB, c = e / NB;
+    if (r >= c) D[c * PLD + r] = (r < nb && c < nb) ? S[(size_t)(k0 + c) * ld + k0 + r] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  if (tid < NB) xd[tid] = 1.0 / D[tid * PLD + tid];
+  __syncthreads();
+  if (warp < 4) {
+    const int b0 = 32 * warp;
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+      for (int p = 0; p < i; ++p) {
+        const double lip = D[(b0 + p) * PLD + b0 + i];
+        if (p & 1) s1 = fma(-lip, x[p], s1); else s0 = fma(-lip, x[p], s0);
+      }
+      x[i] = (s0 + s1) * xd[b0 + i];
+    }
+    __syncwarp();
+    const int c = b0 + lane;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i > lane) D[(b0 + i) * PLD + c] = x[i];
+  }
+  __syncthreads();
+  for (int bi = 1; bi < 4; ++bi) {
+    const int w = 32 * bi;
+    // T[rr][cc] = sum_{p=cc}^{w-1} L[w+rr][p] X[p][cc]; one thread = one row x 4 columns (5 shared loads per 4 FMAs)
+    for (int e = tid; e < 32 * (w / 4); e += PT) {
+      const int rr = e % 32, cc0 = (e / 32) * 4;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      {
+        // triangular corner p = cc0 .. cc0+3: column c takes part from p >= c, X[c][c] = xd[c]
+        const double l0 = D[(cc0 + 0) * PLD + w + rr], l1 = D[(cc0 + 1) * PLD + w + rr];
+        const double l2 = D[(cc0 + 2) * PLD + w + rr], l3 = D[(cc0 + 3) * PLD + w + rr];
+        s0 = l0 * xd[cc0];
+        s0 = fma(l1, D[(cc0 + 1) * PLD + cc0], s0); s1 = l1 * xd[cc0 + 1];
+        s0 = fma(l2, D[(cc0 + 2) * PLD + cc0], s0); s1 = fma(l2, D[(cc0 + 2) * PLD + cc0 + 1], s1); s2 = l2 * xd[cc0 + 2];
+        s0 = fma(l3, D[(cc0 + 3) * PLD + cc0], s0); s1 = fma(l3, D[(cc0 + 3) * PLD + cc0 + 1], s1);
+        s2 = fma(l3, D[(cc0 + 3) * PLD + cc0 + 2], s2); s3 = l3 * xd[cc0 + 3];
+      }
+#pragma unroll 4
+      for (int p = cc0 + 4; p < w; ++p) {
+        const double l = D[p * PLD + w + rr];
+        const double* xp = D + p * PLD + cc0;
+        s0 = fma(l, xp[0], s0); s1 = fma(l, xp[1], s1); s2 = fma(l, xp[2], s2); s3 = fma(l, xp[3], s3);
+      }
+      double* tp = Tm + rr * TLD + cc0;
+      tp[0] = s0; tp[1] = s1; tp[2] = s2; tp[3] = s3;
+    }
+    __syncthreads();
+    // X[w+rr][cc] = -sum_{p<=rr} X_ii[rr][p] T[p][cc]
+    for (int e = tid; e < 32 * (w / 4); e += PT) {
+      const int rr = e % 32, cc0 = (e / 32) * 4;
+      const double xdd = xd[w + rr];
+      const double* tr = Tm + rr * TLD + cc0;
+      double s0 = xdd * tr[0], s1 = xdd * tr[1], s2 = xdd * tr[2], s3 = xdd * tr[3];
+      const double* xi = D + (w + rr) * PLD + w;
+      for (int p = 0; p < rr; ++p) {
+        const double v = xi[p];
+        const double* tq = Tm + p * TLD + cc0;
+        s0 = fma(v, tq[0], s0); s1 = fma(v, tq[1], s1); s2 = fma(v, tq[2], s2); s3 = fma(v, tq[3], s3);
+      }
+      double* o = D + (w + rr) * PLD + cc0;
+      o[0] = -s0; o[1] = -s1; o[2] = -s2; o[3] = -s3;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += PT) {
+    const int r = e % NB, c = e / NB;
+    if (r < c || r >= nb || c >= nb) continue;
+    Linv[(size_t)c * NB + r] = r > c ? D[r * PLD + c] : xd[r];
+  }
+}
+
+// Forward substitution y = L^-1 b in ONE launch, mirror image of k_trsv_bwd_all: CTA j keeps b_j in
+// shared memory, applies b_j -= L_jk y_k for k = 0 .. j-1 as each y_k is published, then y_j = Linv_jj b_j.
+__global__ void __launch_bounds__(TBA_THREADS, 1)
+k_trsv_fwd_all(const double* __restrict__ S, int ld, int n, int T, const double* __restrict__ Linv, const double* __restrict__ b,
+               double* y, int* flags, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double* Lb = sm;                          // Lb[c * NB + r] = L(j0 + r, k0 + c)
+  double* U = Lb + NB * NB;                 // U[c * NB - c (c - 1) / 2 + (r - c)] = Linv_jj(r, c), r >= c
+  double* bj = U + NB * (NB + 1) / 2;
+  double* yk = bj + NB;
+  const int t = threadIdx.x;
+  const int j = (int)blockIdx.x, j0 = j * NB, nbj = min(NB, n - j0);
+  const double* Li = Linv + (size_t)j * NB * NB;
+  for (int c = 0; c < NB; ++c)
+    for (int r = c + t; r < NB; r += TBA_THREADS) U[c * NB - c * (c - 1) / 2 + (r - c)] = Li[(size_t)c * NB + r];
+  if (t < NB) bj[t] = (t < nbj) ? b[j0 + t] : 0.0;
+  __syncthreads();
+  for (int k = 0; k < j; ++k) {
+    const int k0 = k * NB;
+    for (int e = t; e < NB * (NB / 2); e += TBA_THREADS) {
+      const int c = e / (NB / 2), r2 = (e % (NB / 2)) * 2;
+      const double* src = S + (size_t)(k0 + c) * ld + j0 + r2;
+      if (r2 + 1 < nbj) {
+        cp_async16(Lb + c * NB + r2, src, true);
+      } else {
+        if (r2 < nbj) cp_async8(Lb + c * NB + r2, src); else Lb[c * NB + r2] = 0.0;
+        Lb[c * NB + r2 + 1] = 0.0;
+      }
+    }
+    cp_async_commit();
+    if (t == 0) {
+      long long spins = 0;
+      while (ld_acquire(flags + k) == 0) {
+        if (++spins > (1ll << 26)) { atomicCAS(info, 0, -1); break; }
+      }
+    }
+    __syncthreads();
+    if (t < NB) yk[t] = __ldcg(y + k0 + t);             // block k < j is always a full block
+    cp_async_wait<0>();
+    __syncthreads();
+    {
+      const int r = t & 127, h = t >> 7;                 // two threads per row: columns [64 h, 64 h + 64)
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+      for (int c = 64 * h; c < 64 * h + 64; c += 2) {
+        s0 = fma(Lb[c * NB + r], yk[c], s0);
+        s1 = fma(Lb[(c + 1) * NB + r], yk[c + 1], s1);
+      }
+      __syncthreads();
+      if (h == 1) yk[r] = s0 + s1;                       // yk is free again: park the upper half's sum
+      __syncthreads();
+      if (h == 0) bj[r] -= (s0 + s1) + yk[r];
+    }
+    __syncthreads();
+  }
+  {
+    const int r = t & 127, h = t >> 7;                   // y_j = Linv_jj b_j : sum over c <= r, even / odd c
+    double s0 = 0.0;
+    for (int c = h; c <= r; c += 2) s0 = fma(U[c * NB - c * (c - 1) / 2 + (r - c)], bj[c], s0);
+    __syncthreads();
+    if (h == 1) yk[r] = s0;
+    __syncthreads();
+    if (h == 0 && j0 + r < n) y[j0 + r] = s0 + yk[r];
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) st_release(flags + j, 1);
+}
+
 // rhs -> row n of S (the augmented row) and back
 __global__ void k_put_row(double* __restrict__ S, int ld, int n, const double* __restrict__ rhs) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -813,6 +972,51 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
   }
 #endif
   if (n_launches) *n_launches += P->launches;
+  return STBA_OK;
+}
+
+// Both triangular solves on a finished lower Cholesky factor (e.g. cusolverDnDpotrf's): 128 x 128 diagonal
+// inverses (T CTAs side by side), then the one-launch forward and backward substitutions.  cusolverDnDpotrs
+// runs two latency-bound trsv kernels (0.40 + 0.58 ms at n = 5988); this is three launches.
+struct SolvePlan {
+  int n = 0;
+  double* Linv = nullptr;
+  double* ybuf = nullptr;
+  int* flags = nullptr;
+};
+static void destroy_solve(SolvePlan* p) {
+  if (!p) return;
+  if (p->Linv) cudaFree(p->Linv);
+  if (p->ybuf) cudaFree(p->ybuf);
+  if (p->flags) cudaFree(p->flags);
+  delete p;
+}
+SolveWorkspace::~SolveWorkspace() { destroy_solve(plan); }
+
+int chol_solve_with_factor(SolveWorkspace& ws, const double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream,
+                           int* n_launches) {
+  if (n <= 0) return STBA_OK;
+  if (ld % 2) return STBA_ERR_UNSUPPORTED;
+  const int T = (n + NB - 1) / NB;
+  SolvePlan* P = ws.plan;
+  if (!P || P->n != n) {
+    destroy_solve(P);
+    ws.plan = P = new SolvePlan();
+    P->n = n;
+    CKC(cudaMalloc(&P->Linv, (size_t)T * NB * NB * sizeof(double)));
+    CKC(cudaMemset(P->Linv, 0, (size_t)T * NB * NB * sizeof(double)));
+    CKC(cudaMalloc(&P->ybuf, (size_t)T * NB * sizeof(double)));
+    CKC(cudaMalloc(&P->flags, 2 * (size_t)T * sizeof(int)));
+    CKC(cudaFuncSetAttribute(k_inv128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
+    CKC(cudaFuncSetAttribute(k_trsv_fwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM));
+    CKC(cudaFuncSetAttribute(k_trsv_bwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM));
+  }
+  CKC(cudaMemsetAsync(P->flags, 0, 2 * (size_t)T * sizeof(int), stream));
+  k_inv128<<<T, PT, POTRF_SMEM, stream>>>(S, ld, n, P->Linv);
+  k_trsv_fwd_all<<<T, TBA_THREADS, TBA_SMEM, stream>>>(S, ld, n, T, P->Linv, rhs, P->ybuf, P->flags, dev_info);
+  k_trsv_bwd_all<<<T, TBA_THREADS, TBA_SMEM, stream>>>(S, ld, n, T, P->Linv, P->ybuf, rhs, P->flags + T, dev_info);
+  CKC(cudaGetLastError());
+  if (n_launches) *n_launches += 3;
   return STBA_OK;
 }
 

@@ -20,4 +20,14 @@ struct CholWorkspace {
 int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream,
                       int* n_launches);
 
+// The two triangular solves on a finished lower Cholesky factor (column-major, leading dimension ld even) with the
+// one-launch flag-driven substitution kernels of the own back end; used behind cusolverDnDpotrf.
+struct SolvePlan;
+struct SolveWorkspace {
+  SolvePlan* plan = nullptr;
+  ~SolveWorkspace();
+};
+int chol_solve_with_factor(SolveWorkspace& ws, const double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream,
+                           int* n_launches);
+
 }  // namespace stba

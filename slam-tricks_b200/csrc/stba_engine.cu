@@ -125,6 +125,7 @@ struct Engine {
   int potrf_lwork = 0;
   int *dev_info = nullptr, *info_host = nullptr;
   CholWorkspace chol;
+  SolveWorkspace trsv;
   double* flush_buf = nullptr;
   size_t flush_n = 0;
   cudaEvent_t ev[PH_COUNT + 1] = {};
@@ -549,7 +550,7 @@ int Engine::dense_solve(int backend) {
   if (!reduced_built) return STBA_ERR_INVALID_ARGUMENT;
   CK(cudaMemsetAsync(dev_info, 0, sizeof(int), stream));
   if (n > 0) {
-    if (backend == STBA_DENSE_CUSOLVER) {
+    if (backend == STBA_DENSE_CUSOLVER || backend == STBA_DENSE_HYBRID) {
       if (!cusolver) {   // one handle per process and device, created on first use
         DeviceCtx& d = g_dev[device];
         if (!d.cusolver && cusolverDnCreate(&d.cusolver) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
@@ -560,8 +561,14 @@ int Engine::dense_solve(int backend) {
       }
       CKS(cusolverDnSetStream(cusolver, stream));
       CKS(cusolverDnDpotrf(cusolver, CUBLAS_FILL_MODE_LOWER, n, S, ld, potrf_work, potrf_lwork, dev_info));
-      CKS(cusolverDnDpotrs(cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, S, ld, rhs, n, dev_info + 1));
-      launches += 2;
+      if (backend == STBA_DENSE_CUSOLVER) {      // the library's own triangular solves
+        CKS(cusolverDnDpotrs(cusolver, CUBLAS_FILL_MODE_LOWER, n, 1, S, ld, rhs, n, dev_info + 1));
+        launches += 2;
+      } else {                                   // own substitution kernels on the library's factor
+        int nl = 1;
+        CKR(chol_solve_with_factor(trsv, S, n, ld, rhs, dev_info + 1, stream, &nl));
+        launches += nl;
+      }
     } else {
       int nl = 0;
       CKR(chol_factor_solve(chol, S, n, ld, rhs, dev_info, stream, &nl));
@@ -788,7 +795,7 @@ void stba_options_init(stba_options* o) {
   o->update_state_every_iteration = 0;
   o->minimizer_progress_to_stdout = 0;
   o->num_threads = 1;
-  o->dense_backend = STBA_DENSE_CUSOLVER;  // until the own blocked Cholesky is validated on hardware
+  o->dense_backend = STBA_DENSE_HYBRID;    // fastest measured (profiles/r1_dense_notes.md); STBA_DENSE_OWN is all hand-written
   o->initial_trust_region_radius = 1e4;
   o->max_trust_region_radius = 1e16;
   o->min_trust_region_radius = 1e-32;
@@ -971,7 +978,7 @@ int stba_ba_solve(stba_ba* ba, const stba_options* opt, stba_summary* summary, s
 int64_t stba_ba_launch_count(stba_ba* ba) { return ba ? ba->e.launches : 0; }
 
 int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms) {
-  if (!ba || reps < 1 || !ms || phase < 0 || phase > 8) return STBA_ERR_INVALID_ARGUMENT;
+  if (!ba || reps < 1 || !ms || phase < 0 || phase > 9) return STBA_ERR_INVALID_ARGUMENT;
   Engine& e = ba->e;
   CK(cudaSetDevice(e.device));
   stba_options o;
@@ -985,7 +992,7 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
   cudaEvent_t a = e.ev[0], b = e.ev[1];
   for (int r = 0; r < reps; ++r) {
     // preconditions of the phase, untimed
-    if (phase == 4 || phase == 5 || phase == 6 || phase == 7 || phase == 8) CKR(e.build_reduced(1e4, o));
+    if (phase == 4 || phase == 5 || phase == 6 || phase == 7 || phase == 8 || phase == 9) CKR(e.build_reduced(1e4, o));
     if (phase == 5 || phase == 6) CKR(e.dense_solve(o.dense_backend));
     if (phase == 6) CKR(e.step_from_solution());
     if (flush_l2) stba::k_flush<<<e.sm_count * 8, 256, 0, e.stream>>>(e.flush_n, e.flush_buf, (double)r);
@@ -1004,6 +1011,7 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
       case 4: CKR(e.dense_solve(o.dense_backend)); break;
       case 7: CKR(e.dense_solve(STBA_DENSE_OWN)); break;
       case 8: CKR(e.dense_solve(STBA_DENSE_CUSOLVER)); break;
+      case 9: CKR(e.dense_solve(STBA_DENSE_HYBRID)); break;
       case 5: CKR(e.step_from_solution()); break;
       case 6: CKR(e.candidate_cost()); break;
     }
@@ -1106,7 +1114,9 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
   cusolverDnHandle_t h = nullptr;
   int lwork = 0;
   stba::CholWorkspace ws;
-  if (backend == STBA_DENSE_CUSOLVER) {
+  stba::SolveWorkspace tw;
+  const bool lib_factor = backend == STBA_DENSE_CUSOLVER || backend == STBA_DENSE_HYBRID;
+  if (lib_factor) {
     if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
     CKS(cusolverDnSetStream(h, st));
     CKS(cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, n, dS, ld, &lwork));
@@ -1117,9 +1127,14 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
     CK(cudaMemcpyAsync(dr, dr0, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(dinfo, 0, sizeof(int), st));
     CK(cudaEventRecord(a, st));
-    if (backend == STBA_DENSE_CUSOLVER) {
+    if (lib_factor) {
       CKS(cusolverDnDpotrf(h, CUBLAS_FILL_MODE_LOWER, n, dS, ld, work, lwork, dinfo));
-      CKS(cusolverDnDpotrs(h, CUBLAS_FILL_MODE_LOWER, n, 1, dS, ld, dr, n, dinfo + 1));
+      if (backend == STBA_DENSE_CUSOLVER) {
+        CKS(cusolverDnDpotrs(h, CUBLAS_FILL_MODE_LOWER, n, 1, dS, ld, dr, n, dinfo + 1));
+      } else {
+        int nl = 0;
+        rc = stba::chol_solve_with_factor(tw, dS, n, ld, dr, dinfo + 1, st, &nl);
+      }
     } else {
       int nl = 0;
       rc = stba::chol_factor_solve(ws, dS, n, ld, dr, dinfo, st, &nl);

@@ -144,7 +144,7 @@ class BAEngine:
                    "stba_ba_reduced_system")
         return S.T.copy(), rhs     # column-major on the device -> row-major view
 
-    def solve_step(self, dense_backend=capi.DENSE_CUSOLVER):
+    def solve_step(self, dense_backend=capi.DENSE_HYBRID):
         yc = np.empty((self.n_cam, 6)); yl = np.empty((self.n_lm, 3)); mcc = C.c_double(0)
         capi.check(self._L.stba_ba_solve_step(self._h, dense_backend, capi.dptr(yc), capi.dptr(yl), C.byref(mcc)),
                    "stba_ba_solve_step")
@@ -154,7 +154,7 @@ class BAEngine:
         return run_solve(self._L.stba_ba_solve, self._h, options, callback)
 
     # ---- timing ----
-    PHASES = dict(linearize=0, lin_lm=1, lin_cam=2, schur=3, dense=4, backsub=5, cost=6, dense_own=7, dense_cusolver=8)
+    PHASES = dict(linearize=0, lin_lm=1, lin_cam=2, schur=3, dense=4, backsub=5, cost=6, dense_own=7, dense_cusolver=8, dense_hybrid=9)
 
     def time_phase(self, phase, reps=10, flush_l2=False):
         ms = (C.c_float * reps)()

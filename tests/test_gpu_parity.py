@@ -124,11 +124,11 @@ def _compare_solutions(bo, sc, got_state, got_summary, want):
 
 
 @pytest.mark.parametrize("fix", ["scene_small", "scene_B"])
-@pytest.mark.parametrize("backend", ["cusolver", "own"])
+@pytest.mark.parametrize("backend", ["cusolver", "own", "hybrid"])
 def test_full_lm_solve_matches_oracle(stba, bo, fix, backend, request):
     sc = request.getfixturevalue(fix)
     want = bo.solve(*scene_args(sc), backend="c")
-    opt = stba.capi.Options(dense_backend=stba.capi.DENSE_CUSOLVER if backend == "cusolver" else stba.capi.DENSE_OWN)
+    opt = stba.capi.Options(dense_backend={"cusolver": stba.capi.DENSE_CUSOLVER, "own": stba.capi.DENSE_OWN, "hybrid": stba.capi.DENSE_HYBRID}[backend])
     with _engine(stba, sc) as e:
         summ = e.solve(opt)
         _compare_solutions(bo, sc, e.get_state(), summ, want)
@@ -274,14 +274,14 @@ def test_config_C_full_solve_against_golden(stba, scene_C):
 
 # ---- the dense reduced-camera solve in isolation -----------------------------------------------
 @pytest.mark.parametrize("n", [6, 30, 126, 128, 132, 258, 1002, 2994])
-@pytest.mark.parametrize("backend", ["own", "cusolver"])
+@pytest.mark.parametrize("backend", ["own", "cusolver", "hybrid"])
 def test_dense_cholesky_solve(stba, n, backend):
     rng = np.random.default_rng(n)
     A = rng.normal(size=(n, n + 8))
     S = A @ A.T + 1e-3 * n * np.eye(n)
     x_true = rng.normal(size=n)
     rhs = S @ x_true
-    be = stba.capi.DENSE_OWN if backend == "own" else stba.capi.DENSE_CUSOLVER
+    be = {"own": stba.capi.DENSE_OWN, "cusolver": stba.capi.DENSE_CUSOLVER, "hybrid": stba.capi.DENSE_HYBRID}[backend]
     x, info, _ = stba.engine.dense_cholesky_solve(np.tril(S), rhs, be)
     assert info == 0
     x_ref = np.linalg.solve(S, rhs)

@@ -22,7 +22,7 @@ if __name__ == "__main__":
     rhs = rng.normal(size=n)
     ref = None
     for be in a.backends.split(","):
-        x, info, ms = stba.engine.dense_cholesky_solve(np.tril(S), rhs, stba.capi.DENSE_OWN if be == "own" else stba.capi.DENSE_CUSOLVER, reps=a.reps)
+        x, info, ms = stba.engine.dense_cholesky_solve(np.tril(S), rhs, {"own": stba.capi.DENSE_OWN, "cusolver": stba.capi.DENSE_CUSOLVER, "hybrid": stba.capi.DENSE_HYBRID}[be], reps=a.reps)
         res = np.linalg.norm(S @ x - rhs) / np.linalg.norm(rhs)
         gf = (n ** 3 / 3 + 2 * n * n) / 1e9
         best = ms[1:].min() if len(ms) > 1 else ms[0]
