@@ -311,6 +311,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
   CK(cudaMemsetAsync(scal, 0, SC_COUNT * sizeof(double), stream));
   CK(cudaMemsetAsync(dup_flag, 0, 2 * sizeof(int), stream));
+  CK(cudaMemsetAsync(dev_info, 0, 2 * sizeof(int), stream));   // read back by fetch_scalars before the first factorisation
   CK(cudaMemsetAsync(yc, 0, 6 * (size_t)std::max(ncam, 1) * sizeof(double), stream));
 
   tr.mark("cudaMalloc");

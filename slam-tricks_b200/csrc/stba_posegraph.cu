@@ -258,16 +258,24 @@ k_pg_linearize(int n, int B, const double* __restrict__ q, const double* __restr
   cost_share[c] = 0.5 * cost;
 }
 
-// Jacobi scale (first call), LM diagonal, scaled damped band A = S H S + D^2, gs = S g
-__global__ void k_pg_damp(int n, int B, int set_scale, int jacobi, int new_diag, double dmin, double dmax, double inv_radius,
-                          const double* __restrict__ band, const double* __restrict__ g, double* __restrict__ scale,
+// Jacobi column scale 1 / (1 + sqrt(H_kk)), computed once at x0.  Its own launch: k_pg_damp reads the scales of the
+// NEIGHBOURING poses, so they must all exist before it starts (found by a compute-sanitizer run whose timing
+// exposed the race of the first, fused version).
+__global__ void k_pg_scale(int n, int B, int jacobi, const double* __restrict__ band, double* __restrict__ scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const double* col = band + (size_t)c * (B + 1) * 36;
+  for (int k = 0; k < 6; ++k) scale[6 * c + k] = (jacobi && c) ? 1.0 / (1.0 + sqrt(col[7 * k])) : 1.0;
+}
+
+// LM diagonal, scaled damped band A = S H S + D^2, gs = S g
+__global__ void k_pg_damp(int n, int B, int new_diag, double dmin, double dmax, double inv_radius,
+                          const double* __restrict__ band, const double* __restrict__ g, const double* __restrict__ scale,
                           double* __restrict__ diag, double* __restrict__ A, double* __restrict__ gs) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   const double* col = band + (size_t)c * (B + 1) * 36;
   double* out = A + (size_t)c * (B + 1) * 36;
-  if (set_scale)
-    for (int k = 0; k < 6; ++k) scale[6 * c + k] = (jacobi && c) ? 1.0 / (1.0 + sqrt(col[7 * k])) : 1.0;
   double sc[6];
   for (int k = 0; k < 6; ++k) sc[k] = scale[6 * c + k];
   for (int d = 0; d <= B; ++d) {
@@ -620,6 +628,7 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
   CKH(h->alloc(&h->ys, 6 * N)); CKH(h->alloc(&h->scale, 6 * N)); CKH(h->alloc(&h->diag, 6 * N));
   CKH(h->alloc(&h->share, std::max(3 * N, (size_t)M))); CKH(h->alloc(&h->red, 8));
   CKD(cudaMallocHost(&h->red_host, 8 * sizeof(double)));
+  CKD(cudaMemsetAsync(h->red, 0, 8 * sizeof(double), h->s));
   CKD(cudaMemsetAsync(h->ys, 0, 6 * N * sizeof(double), h->s));
   CKD(cudaMemsetAsync(h->gs, 0, 6 * N * sizeof(double), h->s));
   CKD(cudaMemsetAsync(h->diag, 0, 6 * N * sizeof(double), h->s));
@@ -721,9 +730,13 @@ int stba_pg_solve(stba_pg* pg, const stba_options* opt, stba_summary* sum, stba_
     nx.trust_region_radius = radius;
     it = nx;
     // ---- ComputeTrustRegionStep
-    k_pg_damp<<<(n + 127) / 128, 128, 0, pg->s>>>(n, B, pg->have_scale ? 0 : 1, o.jacobi_scaling, reuse ? 0 : 1, o.min_lm_diagonal, o.max_lm_diagonal,
-                                                   1.0 / radius, pg->band, pg->g, pg->scale, pg->diag, pg->A, pg->gs);
-    pg->have_scale = true;
+    if (!pg->have_scale) {
+      k_pg_scale<<<(n + 127) / 128, 128, 0, pg->s>>>(n, B, o.jacobi_scaling, pg->band, pg->scale);
+      ++pg->launches;
+      pg->have_scale = true;
+    }
+    k_pg_damp<<<(n + 127) / 128, 128, 0, pg->s>>>(n, B, reuse ? 0 : 1, o.min_lm_diagonal, o.max_lm_diagonal, 1.0 / radius, pg->band, pg->g,
+                                                   pg->scale, pg->diag, pg->A, pg->gs);
     CK(cudaMemcpyAsync(pg->ys, pg->gs, 6 * (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, pg->s));
     CK(cudaMemsetAsync(pg->info, 0, sizeof(int), pg->s));
     k_pg_band_solve<<<1, BS_THREADS, pg->smem_bytes(), pg->s>>>(n, B, pg->A, pg->ys, pg->info);
