@@ -183,6 +183,7 @@ struct Engine {
   int set_state(const double* h_q, const double* h_t, const double* h_lm);
   int get_state(double* h_q, double* h_t, double* h_lm);
   int linearize();
+  int launch_lin_cam();
   int post_linearize(const stba_options& opt, bool want_grad);
   int build_reduced(double radius, const stba_options& opt);
   int dense_solve(int backend);
@@ -466,6 +467,13 @@ static void launch_lin_lm2(Engine* e, const double* Rt_, const double* lm4_, dou
   ++e->launches;
 }
 
+// camera-major pass
+int Engine::launch_lin_cam() {
+  LAUNCH(this, k_lin_cam2, n_chunk, 32, chunk_cam, chunk_beg, chunk_end, cam_chunk_ptr, cobs_lm, cobs_uv, Rt, lm4, chunk_acc,
+         cam_ticket, Hcc, gc);
+  return STBA_OK;
+}
+
 // residual + Jacobian + J^T J / J^T r blocks at the current x
 int Engine::linearize() {
   if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q, cam_t, Rt);
@@ -479,9 +487,7 @@ int Engine::linearize() {
     CK(cudaMemsetAsync(gc, 0, 6 * (size_t)n_cam * sizeof(double), stream));
   }
   launch_lin_lm2<false>(this, Rt, lm4, Hll, gl, scal + SC_COST);
-  if (n_chunk)
-    LAUNCH(this, k_lin_cam2, n_chunk, 32, chunk_cam, chunk_beg, chunk_end, cam_chunk_ptr, cobs_lm, cobs_uv, Rt, lm4, chunk_acc,
-           cam_ticket, Hcc, gc);
+  if (n_chunk) CKR(launch_lin_cam());
   CK(cudaGetLastError());
   linearized = true;
   reduced_built = false;
@@ -1004,9 +1010,7 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
         stba::launch_lin_lm2<false>(&e, e.Rt, e.lm4, e.Hll, e.gl, e.scal + stba::SC_COST);
         break;
       case 2:
-        if (e.n_chunk)
-          LAUNCH(&e, stba::k_lin_cam2, e.n_chunk, 32, e.chunk_cam, e.chunk_beg, e.chunk_end, e.cam_chunk_ptr, e.cobs_lm, e.cobs_uv, e.Rt,
-                 e.lm4, e.chunk_acc, e.cam_ticket, e.Hcc, e.gc);
+        if (e.n_chunk) CKR(e.launch_lin_cam());
         break;
       case 3: CKR(e.build_reduced(1e4, o)); break;
       case 4: CKR(e.dense_solve(o.dense_backend)); break;
