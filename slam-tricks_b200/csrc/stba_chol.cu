@@ -983,15 +983,17 @@ struct SolvePlan {
   double* Linv = nullptr;
   double* ybuf = nullptr;
   int* flags = nullptr;
+  cudaStream_t stream = nullptr;      // allocations are stream-ordered (pooled): no cudaMalloc / cudaFree stalls per engine
 };
 static void destroy_solve(SolvePlan* p) {
   if (!p) return;
-  if (p->Linv) cudaFree(p->Linv);
-  if (p->ybuf) cudaFree(p->ybuf);
-  if (p->flags) cudaFree(p->flags);
+  if (p->Linv) cudaFreeAsync(p->Linv, p->stream);
+  if (p->ybuf) cudaFreeAsync(p->ybuf, p->stream);
+  if (p->flags) cudaFreeAsync(p->flags, p->stream);
   delete p;
 }
-SolveWorkspace::~SolveWorkspace() { destroy_solve(plan); }
+SolveWorkspace::~SolveWorkspace() { reset(); }
+void SolveWorkspace::reset() { destroy_solve(plan); plan = nullptr; }
 
 int chol_solve_with_factor(SolveWorkspace& ws, const double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream,
                            int* n_launches) {
@@ -1003,10 +1005,11 @@ int chol_solve_with_factor(SolveWorkspace& ws, const double* S, int n, int ld, d
     destroy_solve(P);
     ws.plan = P = new SolvePlan();
     P->n = n;
-    CKC(cudaMalloc(&P->Linv, (size_t)T * NB * NB * sizeof(double)));
-    CKC(cudaMemset(P->Linv, 0, (size_t)T * NB * NB * sizeof(double)));
-    CKC(cudaMalloc(&P->ybuf, (size_t)T * NB * sizeof(double)));
-    CKC(cudaMalloc(&P->flags, 2 * (size_t)T * sizeof(int)));
+    P->stream = stream;
+    CKC(cudaMallocAsync((void**)&P->Linv, (size_t)T * NB * NB * sizeof(double), stream));
+    CKC(cudaMemsetAsync(P->Linv, 0, (size_t)T * NB * NB * sizeof(double), stream));
+    CKC(cudaMallocAsync((void**)&P->ybuf, (size_t)T * NB * sizeof(double), stream));
+    CKC(cudaMallocAsync((void**)&P->flags, 2 * (size_t)T * sizeof(int), stream));
     CKC(cudaFuncSetAttribute(k_inv128, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM));
     CKC(cudaFuncSetAttribute(k_trsv_fwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM));
     CKC(cudaFuncSetAttribute(k_trsv_bwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM));

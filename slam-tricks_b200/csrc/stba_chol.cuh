@@ -26,6 +26,7 @@ struct SolvePlan;
 struct SolveWorkspace {
   SolvePlan* plan = nullptr;
   ~SolveWorkspace();
+  void reset();               // release the stream-ordered buffers (before the stream they were allocated on is destroyed)
 };
 int chol_solve_with_factor(SolveWorkspace& ws, const double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream,
                            int* n_launches);

@@ -165,6 +165,7 @@ struct Engine {
   }
   ~Engine() {
     chol.reset();   // the captured graph references this engine's buffers
+    trsv.reset();   // stream-ordered buffers: free them while the stream still exists
     if (stream) {
       for (void* p : allocs) cudaFreeAsync(p, stream);
       cudaStreamSynchronize(stream);
@@ -533,6 +534,7 @@ int Engine::build_reduced(double radius, const stba_options& opt) {
   if (n_cam) LAUNCH(this, k_cam_diag, (6 * n_cam + 127) / 128, 128, n_cam, Hcc, sc, opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dc2);
   LAUNCH(this, k_schur_lm, grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, obs_uv, Rt, lm4, cam_const, lc, Hll, gl, sl,
          opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dl2, Linv, hl, E);
+  if (n_obs) LAUNCH(this, k_schur_E, grid_for(n_obs, kBlock), kBlock, n_obs, obs_cam, obs_lm, obs_uv, Rt, lm4, cam_const, lc, Linv, E);
   if (n_free) {
     if (n_chunk)
       LAUNCH(this, k_schur_diag, n_chunk, 32, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
@@ -1152,6 +1154,8 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
     CK(cudaMemcpy(x, dr, n * sizeof(double), cudaMemcpyDeviceToHost));
     if (info) CK(cudaMemcpy(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost));
   }
+  tw.reset();
+  cudaStreamSynchronize(st);
   if (h) cusolverDnDestroy(h);
   cudaFree(dS); cudaFree(dS0); cudaFree(dr); cudaFree(dr0); cudaFree(dinfo); if (work) cudaFree(work);
   cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(st);

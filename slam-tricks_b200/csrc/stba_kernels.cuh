@@ -84,15 +84,11 @@ k_schur_lm(int n_lm, const int* __restrict__ lm_ptr, const int* __restrict__ obs
            double inv_radius, double* __restrict__ Dl2, double* __restrict__ Linv,
            double* __restrict__ hl, double* __restrict__ E) {
   for (int l = blockIdx.x * kBlock + threadIdx.x; l < n_lm; l += gridDim.x * kBlock) {
-    const int beg = lm_ptr[l], end = lm_ptr[l + 1];
     if (lm_const && lm_const[l]) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) Linv[6 * (size_t)l + k] = 0.0;
 #pragma unroll
       for (int k = 0; k < 3; ++k) { hl[3 * (size_t)l + k] = 0.0; Dl2[3 * (size_t)l + k] = 0.0; }
-      for (int o = beg; o < end; ++o)
-#pragma unroll
-        for (int k = 0; k < 18; ++k) E[18 * (size_t)o + k] = 0.0;
       continue;
     }
     const double* H = Hll + 6 * (size_t)l;
@@ -119,43 +115,54 @@ k_schur_lm(int n_lm, const int* __restrict__ lm_ptr, const int* __restrict__ obs
     hl[3 * (size_t)l + 1] = m10 * g0 + m11 * g1;
     hl[3 * (size_t)l + 2] = m20 * g0 + m21 * g1 + m22 * g2;
 
+  }
+}
+
+// E per observation, one thread per OBSERVATION (ten times the parallelism of walking a landmark's
+// observations in its thread: the camera-tile gather is the latency, occupancy hides it):
+//   E = W L^-T,  W = Jc^T Jl,  L L^T = H_ll + D_l^2  (Linv from k_schur_lm)
+__global__ void __launch_bounds__(kBlock)
+k_schur_E(int64_t n_obs, const int* __restrict__ obs_cam, const int* __restrict__ obs_lm, const double* __restrict__ obs_uv,
+          const double* __restrict__ Rt, const double* __restrict__ lm4, const uint8_t* __restrict__ cam_const,
+          const uint8_t* __restrict__ lm_const, const double* __restrict__ Linv, double* __restrict__ E) {
+  for (int64_t o = blockIdx.x * (int64_t)kBlock + threadIdx.x; o < n_obs; o += (int64_t)gridDim.x * kBlock) {
+    const int c = __ldg(obs_cam + o), l = __ldg(obs_lm + o);
+    double2* Eo = reinterpret_cast<double2*>(E + 18 * (size_t)o);
+    if (cam_const[c] || (lm_const && lm_const[l])) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Eo[k] = make_double2(0.0, 0.0);
+      continue;
+    }
+    const double2 uv = ldg2(obs_uv + 2 * (size_t)o);
     const double2 pxy = ldg2(lm4 + 4 * (size_t)l);
     const double pz = __ldg(lm4 + 4 * (size_t)l + 2);
-    for (int o = beg; o < end; ++o) {
-      const int c = __ldg(obs_cam + o);
-      double2* Eo = reinterpret_cast<double2*>(E + 18 * (size_t)o);
-      if (cam_const[c]) {
+    const double2 ma = ldg2(Linv + 6 * (size_t)l), mb = ldg2(Linv + 6 * (size_t)l + 2), mc = ldg2(Linv + 6 * (size_t)l + 4);
+    const double m00 = ma.x, m10 = ma.y, m11 = mb.x, m20 = mb.y, m21 = mc.x, m22 = mc.y;
+    double T[kCamVals];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) Eo[k] = make_double2(0.0, 0.0);
-        continue;
-      }
-      const double2 uv = ldg2(obs_uv + 2 * (size_t)o);
-      double T[kCamVals];
-#pragma unroll
-      for (int k = 0; k < kCamVals; k += 2) {
-        const double2 x = ldg2(Rt + (size_t)kCamTile * c + k);
-        T[k] = x.x; T[k + 1] = x.y;
-      }
-      const Obs ob = project(T, pxy.x, pxy.y, pz, uv.x, uv.y);
-      double J0[3], J1[3], T0[3], T1[3];
-      landmark_jacobian(T, ob, J0, J1);
-      rotation_jacobian(ob, T0, T1);
-      // Z = Jl Linv^T  (2x3):  Z[r][k] = sum_{j<=k} Jl[r][j] Linv[k][j]
-      const double z00 = J0[0] * m00, z01 = J0[0] * m10 + J0[1] * m11, z02 = J0[0] * m20 + J0[1] * m21 + J0[2] * m22;
-      const double z10 = J1[0] * m00, z11 = J1[0] * m10 + J1[1] * m11, z12 = J1[0] * m20 + J1[1] * m21 + J1[2] * m22;
-      double e[18];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {           // E_theta = J_th^T Z ; E_t = -Jl^T Z
-        e[3 * i + 0] = T0[i] * z00 + T1[i] * z10;
-        e[3 * i + 1] = T0[i] * z01 + T1[i] * z11;
-        e[3 * i + 2] = T0[i] * z02 + T1[i] * z12;
-        e[9 + 3 * i + 0] = -(J0[i] * z00 + J1[i] * z10);
-        e[9 + 3 * i + 1] = -(J0[i] * z01 + J1[i] * z11);
-        e[9 + 3 * i + 2] = -(J0[i] * z02 + J1[i] * z12);
-      }
-#pragma unroll
-      for (int k = 0; k < 9; ++k) Eo[k] = make_double2(e[2 * k], e[2 * k + 1]);
+    for (int k = 0; k < kCamVals; k += 2) {
+      const double2 x = ldg2(Rt + (size_t)kCamTile * c + k);
+      T[k] = x.x; T[k + 1] = x.y;
     }
+    const Obs ob = project(T, pxy.x, pxy.y, pz, uv.x, uv.y);
+    double J0[3], J1[3], T0[3], T1[3];
+    landmark_jacobian(T, ob, J0, J1);
+    rotation_jacobian(ob, T0, T1);
+    // Z = Jl Linv^T  (2x3):  Z[r][k] = sum_{j<=k} Jl[r][j] Linv[k][j]
+    const double z00 = J0[0] * m00, z01 = J0[0] * m10 + J0[1] * m11, z02 = J0[0] * m20 + J0[1] * m21 + J0[2] * m22;
+    const double z10 = J1[0] * m00, z11 = J1[0] * m10 + J1[1] * m11, z12 = J1[0] * m20 + J1[1] * m21 + J1[2] * m22;
+    double e[18];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {           // E_theta = J_th^T Z ; E_t = -Jl^T Z
+      e[3 * i + 0] = T0[i] * z00 + T1[i] * z10;
+      e[3 * i + 1] = T0[i] * z01 + T1[i] * z11;
+      e[3 * i + 2] = T0[i] * z02 + T1[i] * z12;
+      e[9 + 3 * i + 0] = -(J0[i] * z00 + J1[i] * z10);
+      e[9 + 3 * i + 1] = -(J0[i] * z01 + J1[i] * z11);
+      e[9 + 3 * i + 2] = -(J0[i] * z02 + J1[i] * z12);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Eo[k] = make_double2(e[2 * k], e[2 * k + 1]);
   }
 }
 
