@@ -467,6 +467,296 @@ k_pg_band_solve(int n, int B, double* __restrict__ A, double* __restrict__ y, in
   }
 }
 
+// ---- partitioned band solve (more than one SM) ---------------------------------------------------
+// The block columns are cut into P interiors I_p separated by separators S_p of exactly B block columns, so
+// that two interiors never couple directly.  With the interiors ordered first the matrix is
+// [[A_II, A_IS], [A_SI, A_SS]] with A_II block diagonal, and
+//   k_pg_part_rhs      Z_p <- [b_I | A_{I,S_{p-1}} | A_{I,S_p}]                       (right-hand sides + spikes)
+//   k_pg_part_factor   banded Cholesky of every interior side by side (one CTA each, the ring kernel above
+//                      with 1 + 12 B right-hand-side columns): Z_p <- L_p^-1 Z_p
+//   k_pg_part_gram     G_p = Z_p^T Z_p
+//   k_pg_part_assemble reduced system over the separators, R = A_SS - sum_p (spike Gram blocks): block banded with
+//                      half-bandwidth 2B - 1, in the same band layout
+//   k_pg_band_solve    the reduced system, on one SM (P B columns instead of N)
+//   k_pg_part_back     x_I = L_p^-T (z_p - W_l x_{S_{p-1}} - W_r x_{S_p}), every interior side by side
+// Exact (same factorisation in another elimination order); the serial depth drops from N to N / P + P B.
+__device__ __forceinline__ void cp_async8_zfill(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+
+__global__ void __launch_bounds__(256)
+k_pg_part_rhs(int B, int P, const int* __restrict__ pi0, const int* __restrict__ pi1, const double* __restrict__ A,
+              const double* __restrict__ y, double* __restrict__ Z) {
+  const int p = blockIdx.x, i0 = pi0[p], i1 = pi1[p], CB = (B + 1) * 36, Rw = 1 + 12 * B;
+  const int total = (i1 - i0) * 6 * Rw;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int c = i0 + e / (6 * Rw), a = (e / Rw) % 6, col = e % Rw;
+    double v = 0.0;
+    if (col == 0) {
+      v = y[6 * (size_t)c + a];
+    } else if (col < 1 + 6 * B) {
+      const int j = col - 1, s = i0 - B + j / 6, k = j % 6;             // left separator column s, block (c, s)[a][k]
+      if (p > 0 && c - s <= B) v = A[(size_t)s * CB + (c - s) * 36 + a * 6 + k];
+    } else {
+      const int j = col - 1 - 6 * B, s = i1 + j / 6, k = j % 6;         // right separator column s, block (s, c)[k][a]
+      if (p < P - 1 && s - c <= B) v = A[(size_t)c * CB + (s - c) * 36 + k * 6 + a];
+    }
+    Z[(size_t)c * 6 * Rw + a * Rw + col] = v;
+  }
+}
+
+__global__ void __launch_bounds__(BS_THREADS, 1)
+k_pg_part_factor(int B, const int* __restrict__ pi0, const int* __restrict__ pi1, double* __restrict__ A, double* __restrict__ Z,
+                 int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  const int Wn = B + 3, CB = (B + 1) * 36, Rw = 1 + 12 * B, YB = 6 * Rw;
+  double* W = sm;                                       // W[slot][d][36]
+  double* Lc = W + (size_t)Wn * CB;                     // Lc[d][36]
+  double* Li = Lc + (size_t)(B + 1) * 36;
+  double* yw = Li + 36;                                 // rhs ring yw[slot][6][Rw]
+  double* yc = yw + (size_t)Wn * YB;                    // y_c [6][Rw]
+  const int tid = threadIdx.x, i0 = pi0[blockIdx.x], i1 = pi1[blockIdx.x];
+  auto load_col = [&](int c) {
+    if (c < i1) {
+      const int s = c % Wn;
+      // blocks whose row lies outside the interior belong to the spikes, not to A_II: they enter as zeros
+      for (int e = tid; e < CB; e += BS_THREADS) cp_async8_zfill(W + (size_t)s * CB + e, A + (size_t)c * CB + e, c + e / 36 < i1);
+      for (int e = tid; e < YB; e += BS_THREADS) cp_async8(yw + (size_t)s * YB + e, Z + (size_t)c * YB + e);
+    }
+    cp_async_commit();
+  };
+  for (int c = i0; c < i0 + B + 2; ++c) load_col(c);
+  for (int c = i0; c < i1; ++c) {
+    cp_async_wait<1>();
+    __syncthreads();
+    double* Wc = W + (size_t)(c % Wn) * CB;
+    if (tid == 0) {
+      double L[21];
+#define LL(i, j) L[(i) * ((i) + 1) / 2 + (j)]
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) LL(i, j) = Wc[6 * i + j];
+#pragma unroll
+      for (int k = 0; k < 36; ++k) Li[k] = 0.0;
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        double d = LL(j, j);
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= LL(j, k) * LL(j, k);
+        if (!(d > 0.0) && ok) { ok = false; atomicCAS(info, 0, 6 * c + j + 1); }
+        const double inv = fast_rsqrt(d);
+        LL(j, j) = inv;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+          double s = LL(i, j);
+#pragma unroll
+          for (int k = 0; k < j; ++k) s -= LL(i, k) * LL(j, k);
+          LL(i, j) = s * inv;
+        }
+      }
+      double X[21];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        X[j * (j + 1) / 2 + j] = LL(j, j);
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = j; k < i; ++k) s -= LL(i, k) * X[k * (k + 1) / 2 + j];
+          X[i * (i + 1) / 2 + j] = s * LL(i, i);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) Li[6 * i + j] = X[i * (i + 1) / 2 + j];
+#undef LL
+    }
+    __syncthreads();
+    // P2: L_{c+d,c} = A_{c+d,c} L_cc^-T ; y_c = L_cc^-1 Y_c  (6 x Rw)
+    for (int e = tid; e < 36 * B; e += BS_THREADS) {
+      const int d = 1 + e / 36, a = (e % 36) / 6, b = e % 6;
+      double s = 0.0;
+      for (int k = 0; k <= b; ++k) s += Wc[d * 36 + 6 * a + k] * Li[6 * b + k];
+      Lc[d * 36 + 6 * a + b] = s;
+    }
+    {
+      const double* Yc = yw + (size_t)(c % Wn) * YB;
+      for (int e = tid; e < YB; e += BS_THREADS) {
+        const int a = e / Rw, col = e % Rw;
+        double s = 0.0;
+        for (int k = 0; k <= a; ++k) s += Li[6 * a + k] * Yc[k * Rw + col];
+        yc[e] = s;
+      }
+    }
+    __syncthreads();
+    // P3: trailing update and right-hand-side update inside the interior, factor column and y_c out, next column in
+    const int npair = B * (B + 1) / 2;
+    for (int e = tid; e < 36 * npair; e += BS_THREADS) {
+      int pp = e / 36, d2 = 1;
+      while (pp >= B - d2 + 1) { pp -= B - d2 + 1; ++d2; }
+      const int d1 = d2 + pp, a = (e % 36) / 6, b = e % 6;
+      if (c + d1 < i1) {
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += Lc[d1 * 36 + 6 * a + k] * Lc[d2 * 36 + 6 * b + k];
+        W[(size_t)((c + d2) % Wn) * CB + (d1 - d2) * 36 + 6 * a + b] -= s;
+      }
+    }
+    for (int e = tid; e < B * YB; e += BS_THREADS) {
+      const int d = 1 + e / YB, r = e % YB, a = r / Rw, col = r % Rw;
+      if (c + d < i1) {
+        double s = 0.0;
+        for (int k = 0; k < 6; ++k) s += Lc[d * 36 + 6 * a + k] * yc[k * Rw + col];
+        yw[(size_t)((c + d) % Wn) * YB + r] -= s;
+      }
+    }
+    for (int e = tid; e < CB; e += BS_THREADS) {
+      // rows outside the interior keep their original (spike) blocks in A: only the interior part is overwritten
+      if (e < 36) A[(size_t)c * CB + e] = Li[e];
+      else if (c + e / 36 < i1) A[(size_t)c * CB + e] = Lc[e];
+    }
+    for (int e = tid; e < YB; e += BS_THREADS) Z[(size_t)c * YB + e] = yc[e];
+    __syncthreads();
+    load_col(c + B + 2);
+  }
+  cp_async_wait<0>();
+}
+
+// G_p = Z_p^T Z_p  (Rw x Rw), rows streamed through shared memory in tiles of 32
+__global__ void __launch_bounds__(256)
+k_pg_part_gram(int B, const int* __restrict__ pi0, const int* __restrict__ pi1, const double* __restrict__ Z, double* __restrict__ G) {
+  extern __shared__ __align__(16) double sm[];          // tile[32][Rw]
+  const int p = blockIdx.x, Rw = 1 + 12 * B, rows = 6 * (pi1[p] - pi0[p]);
+  const double* Zp = Z + (size_t)pi0[p] * 6 * Rw;
+  const int n_ent = Rw * Rw;
+  constexpr int MAXE = 40;                              // entries per thread: Rw^2 / 256 <= 9409 / 256 for B = 8
+  double acc[MAXE];
+#pragma unroll
+  for (int k = 0; k < MAXE; ++k) acc[k] = 0.0;
+  for (int r0 = 0; r0 < rows; r0 += 32) {
+    const int nr = min(32, rows - r0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * Rw; e += 256) sm[e] = Zp[(size_t)r0 * Rw + e];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < MAXE; ++k) {
+      const int e = threadIdx.x + 256 * k;
+      if (e < n_ent) {
+        const int i = e / Rw, j = e % Rw;
+        double s = acc[k];
+        for (int r = 0; r < nr; ++r) s = fma(sm[r * Rw + i], sm[r * Rw + j], s);
+        acc[k] = s;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < MAXE; ++k) {
+    const int e = threadIdx.x + 256 * k;
+    if (e < n_ent) G[(size_t)p * n_ent + e] = acc[k];
+  }
+}
+
+// reduced band Rb (block column rc = p B + sl, half-bandwidth Br = 2B - 1) and reduced right-hand side, one CTA per separator
+__global__ void __launch_bounds__(256)
+k_pg_part_assemble(int B, int P, const int* __restrict__ pi1, const double* __restrict__ A, const double* __restrict__ y,
+                   const double* __restrict__ G, double* __restrict__ Rb, double* __restrict__ yR) {
+  const int p = blockIdx.x;                             // separator p: between interiors p and p + 1
+  const int CB = (B + 1) * 36, Rw = 1 + 12 * B, Br = 2 * B - 1, CBr = (Br + 1) * 36, s0 = pi1[p];
+  const double* Gl = G + (size_t)p * Rw * Rw;           // interior p: this separator is its RIGHT one  (columns 1 + 6B ..)
+  const double* Gr = G + (size_t)(p + 1) * Rw * Rw;     // interior p + 1: this separator is its LEFT one (columns 1 ..)
+  const int oR = 1 + 6 * B, oL = 1;
+  // (i) blocks inside the separator: rows (sl2, a), cols (sl1, k), sl2 >= sl1
+  for (int e = threadIdx.x; e < B * B * 36; e += 256) {
+    const int sl2 = e / (B * 36), sl1 = (e / 36) % B, a = (e % 36) / 6, k = e % 6;
+    if (sl2 < sl1) continue;
+    const double v = A[(size_t)(s0 + sl1) * CB + (sl2 - sl1) * 36 + a * 6 + k]
+                     - Gl[(size_t)(oR + sl2 * 6 + a) * Rw + oR + sl1 * 6 + k] - Gr[(size_t)(oL + sl2 * 6 + a) * Rw + oL + sl1 * 6 + k];
+    Rb[(size_t)(p * B + sl1) * CBr + (sl2 - sl1) * 36 + a * 6 + k] = v;
+  }
+  // (ii) coupling with the previous separator through interior p: rows (p, sl2), cols (p - 1, sl1)
+  if (p > 0) {
+    for (int e = threadIdx.x; e < B * B * 36; e += 256) {
+      const int sl2 = e / (B * 36), sl1 = (e / 36) % B, a = (e % 36) / 6, k = e % 6;
+      const double v = -Gl[(size_t)(oR + sl2 * 6 + a) * Rw + oL + sl1 * 6 + k];
+      Rb[(size_t)((p - 1) * B + sl1) * CBr + (B + sl2 - sl1) * 36 + a * 6 + k] = v;
+    }
+  }
+  for (int e = threadIdx.x; e < 6 * B; e += 256)
+    yR[(size_t)p * 6 * B + e] = y[6 * (size_t)s0 + e] - Gl[(size_t)(oR + e) * Rw] - Gr[(size_t)(oL + e) * Rw];
+}
+
+__global__ void __launch_bounds__(BS_THREADS, 1)
+k_pg_part_back(int B, int P, const int* __restrict__ pi0, const int* __restrict__ pi1, const double* __restrict__ A,
+               const double* __restrict__ Z, const double* __restrict__ yR, double* __restrict__ y) {
+  extern __shared__ __align__(16) double sm[];
+  const int Wn = B + 3, CB = (B + 1) * 36, Rw = 1 + 12 * B, YB = 6 * Rw;
+  double* W = sm;
+  double* xw = W + (size_t)Wn * CB;                     // x ring [Wn][6]
+  double* ps = xw + (size_t)Wn * 6;                     // partial sums [6 (B + 1)]
+  double* yc = ps + 6 * (B + 1);
+  double* xs = yc + 6;                                  // [12 B]: solutions of the left and right separators
+  const int tid = threadIdx.x, p = blockIdx.x, i0 = pi0[p], i1 = pi1[p];
+  for (int e = tid; e < 12 * B; e += BS_THREADS) {
+    const bool left = e < 6 * B;
+    const int j = left ? e : e - 6 * B;
+    double v = 0.0;
+    if (left && p > 0) v = yR[(size_t)(p - 1) * 6 * B + j];
+    if (!left && p < P - 1) v = yR[(size_t)p * 6 * B + j];
+    xs[e] = v;
+    if (!left && p < P - 1) y[6 * (size_t)i1 + j] = v;  // this CTA also publishes its right separator's solution
+  }
+  __syncthreads();
+  // t = z - W_l x_l - W_r x_r, written over y (the backward substitution below reads it from there)
+  for (int e = tid; e < 6 * (i1 - i0); e += BS_THREADS) {
+    const double* z = Z + (size_t)i0 * YB + (size_t)(e / 6) * YB + (e % 6) * Rw;
+    double s = z[0];
+    for (int j = 0; j < 12 * B; ++j) s = fma(-z[1 + j], xs[j], s);
+    y[6 * (size_t)i0 + e] = s;
+  }
+  __syncthreads();
+  auto load_back = [&](int c) {
+    if (c >= i0) {
+      const int s = c % Wn;
+      for (int e = tid; e < CB; e += BS_THREADS) cp_async8(W + (size_t)s * CB + e, A + (size_t)c * CB + e);
+    }
+    cp_async_commit();
+  };
+  load_back(i1 - 1);
+  load_back(i1 - 2);
+  for (int c = i1 - 1; c >= i0; --c) {
+    cp_async_wait<1>();
+    __syncthreads();
+    const double* Ac = W + (size_t)(c % Wn) * CB;
+    if (tid < 6 * (B + 1)) {
+      const int d = tid / 6, a = tid % 6;
+      double s = 0.0;
+      if (d >= 1 && c + d < i1) {
+        for (int k = 0; k < 6; ++k) s += Ac[d * 36 + 6 * k + a] * xw[((c + d) % Wn) * 6 + k];
+      }
+      ps[tid] = s;
+    }
+    __syncthreads();
+    if (tid < 6) {
+      double s = y[6 * (size_t)c + tid];
+      for (int d = 1; d <= B; ++d) s -= ps[d * 6 + tid];
+      yc[tid] = s;
+    }
+    __syncthreads();
+    if (tid < 6) {
+      double s = 0.0;
+      for (int k = tid; k < 6; ++k) s += Ac[6 * k + tid] * yc[k];
+      xw[(c % Wn) * 6 + tid] = s;
+      y[6 * (size_t)c + tid] = s;
+    }
+    load_back(c - 2);
+  }
+  cp_async_wait<0>();
+}
+
 // step: delta = -ys * scale, candidate T+ = T Exp(delta); per-pose shares of |step|^2, |x+|... and of the model cost change
 __global__ void k_pg_update(int n, const double* __restrict__ q, const double* __restrict__ t, const double* __restrict__ ys,
                             const double* __restrict__ scale, const double* __restrict__ gs, const double* __restrict__ diag,
