@@ -842,6 +842,10 @@ struct stba_pg {
   double *band = nullptr, *A = nullptr, *g = nullptr, *gs = nullptr, *ys = nullptr, *scale = nullptr, *diag = nullptr;
   double *share = nullptr, *red = nullptr, *red_host = nullptr;
   bool have_scale = false;
+  // partitioned band solve (P > 1): interiors [pi0, pi1), separators of B columns in between
+  int P = 1, Br = 1;
+  int *pi0 = nullptr, *pi1 = nullptr;
+  double *Z = nullptr, *G = nullptr, *Rb = nullptr, *yR = nullptr;
   std::vector<void*> allocs;
   template <typename T>
   int alloc(T** p, size_t count) {
@@ -856,7 +860,29 @@ struct stba_pg {
     if (red_host) cudaFreeHost(red_host);
     if (s) cudaStreamDestroy(s);
   }
-  int smem_bytes() const { return (int)(((size_t)(B + 3) * (B + 1) * 36 + (size_t)(B + 1) * 36 + 36 + (size_t)(B + 3) * 6 + 6) * sizeof(double)); }
+  static int band_smem(int b) { return (int)(((size_t)(b + 3) * (b + 1) * 36 + (size_t)(b + 1) * 36 + 36 + (size_t)(b + 3) * 6 + 6) * sizeof(double)); }
+  int smem_bytes() const { return band_smem(std::max(B, Br)); }
+  int factor_smem() const { const int Rw = 1 + 12 * B; return (int)(((size_t)(B + 3) * (B + 1) * 36 + (size_t)(B + 1) * 36 + 36 + (size_t)(B + 4) * 6 * Rw) * sizeof(double)); }
+  int back_smem() const { return (int)(((size_t)(B + 3) * (B + 1) * 36 + (size_t)(B + 3) * 6 + 6 * (B + 1) + 6 + 12 * B) * sizeof(double)); }
+
+  // solve A ys = ys in place (A = scaled damped band); info <- first non-positive pivot
+  int band_solve() {
+    if (P <= 1) {
+      k_pg_band_solve<<<1, BS_THREADS, band_smem(B), s>>>(n, B, A, ys, info);
+      ++launches;
+      return STBA_OK;
+    }
+    const int Rw = 1 + 12 * B;
+    k_pg_part_rhs<<<P, 256, 0, s>>>(B, P, pi0, pi1, A, ys, Z);
+    k_pg_part_factor<<<P, BS_THREADS, factor_smem(), s>>>(B, pi0, pi1, A, Z, info);
+    k_pg_part_gram<<<P, 256, 32 * Rw * (int)sizeof(double), s>>>(B, pi0, pi1, Z, G);
+    CK(cudaMemsetAsync(Rb, 0, (size_t)(P - 1) * B * (Br + 1) * 36 * sizeof(double), s));
+    k_pg_part_assemble<<<P - 1, 256, 0, s>>>(B, P, pi1, A, ys, G, Rb, yR);
+    k_pg_band_solve<<<1, BS_THREADS, band_smem(Br), s>>>((P - 1) * B, Br, Rb, yR, info);
+    k_pg_part_back<<<P, BS_THREADS, back_smem(), s>>>(B, P, pi0, pi1, A, Z, yR, ys);
+    launches += 6;
+    return STBA_OK;
+  }
 
   int linearize(double* cost) {
     k_pg_linearize<<<(n + 63) / 64, 64, 0, s>>>(n, B, q, t, inc_ptr, inc_edge, ei, ej, zq, zt, band, g, share);
@@ -933,6 +959,37 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
     CKD(cudaMemcpyAsync(h->inc_edge, inc.data(), inc.size() * sizeof(int), cudaMemcpyHostToDevice, h->s));
   }
   CKD(cudaMemcpyAsync(h->inc_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, h->s));
+  {
+    // partitions: serial depth N / P + P B is smallest near P = sqrt(N / B); every interior must be at least B
+    // columns long (so that interiors never couple) and the reduced half-bandwidth 2B - 1 must fit the ring
+    int P = 1;
+    if (!getenv("STBA_PG_SERIAL") && 2 * B - 1 <= kMaxBand && n_poses >= 64 * B) {
+      cudaDeviceProp prop;
+      CKD(cudaGetDeviceProperties(&prop, device));
+      P = (int)std::lround(std::sqrt((double)n_poses / B));
+      P = std::max(1, std::min(P, prop.multiProcessorCount));
+    }
+    if (const char* ov = getenv("STBA_PG_PARTS")) P = (2 * B - 1 <= kMaxBand) ? std::max(1, atoi(ov)) : 1;    // tests: force a partition count
+    while (P > 1 && (n_poses - (P - 1) * B) / P < std::max(B, 8)) --P;
+    h->P = P;
+    h->Br = P > 1 ? 2 * B - 1 : 1;
+    if (P > 1) {
+      std::vector<int> i0(P), i1(P);
+      const int m = n_poses - (P - 1) * B, base = m / P, rem = m % P;
+      int c = 0;
+      for (int p = 0; p < P; ++p) { i0[p] = c; c += base + (p < rem ? 1 : 0); i1[p] = c; if (p < P - 1) c += B; }
+      const size_t Rw = 1 + 12 * (size_t)B;
+      CKH(h->alloc(&h->pi0, P)); CKH(h->alloc(&h->pi1, P));
+      CKH(h->alloc(&h->Z, N * 6 * Rw)); CKH(h->alloc(&h->G, (size_t)P * Rw * Rw));
+      CKH(h->alloc(&h->Rb, (size_t)(P - 1) * B * (h->Br + 1) * 36)); CKH(h->alloc(&h->yR, (size_t)(P - 1) * B * 6));
+      CKD(cudaMemcpyAsync(h->pi0, i0.data(), P * sizeof(int), cudaMemcpyHostToDevice, h->s));
+      CKD(cudaMemcpyAsync(h->pi1, i1.data(), P * sizeof(int), cudaMemcpyHostToDevice, h->s));
+      CKD(cudaStreamSynchronize(h->s));       // i0 / i1 are stack vectors
+      CKD(cudaFuncSetAttribute(k_pg_part_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, h->factor_smem()));
+      CKD(cudaFuncSetAttribute(k_pg_part_back, cudaFuncAttributeMaxDynamicSharedMemorySize, h->back_smem()));
+      CKD(cudaFuncSetAttribute(k_pg_part_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (int)Rw * (int)sizeof(double)));
+    }
+  }
   CKD(cudaFuncSetAttribute(k_pg_band_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes()));
   CKD(cudaStreamSynchronize(h->s));
 #undef CKH
@@ -1029,12 +1086,12 @@ int stba_pg_solve(stba_pg* pg, const stba_options* opt, stba_summary* sum, stba_
                                                    pg->scale, pg->diag, pg->A, pg->gs);
     CK(cudaMemcpyAsync(pg->ys, pg->gs, 6 * (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, pg->s));
     CK(cudaMemsetAsync(pg->info, 0, sizeof(int), pg->s));
-    k_pg_band_solve<<<1, BS_THREADS, pg->smem_bytes(), pg->s>>>(n, B, pg->A, pg->ys, pg->info);
+    if ((r = pg->band_solve()) != STBA_OK) return r;
     k_pg_update<<<(n + 127) / 128, 128, 0, pg->s>>>(n, pg->q, pg->t, pg->ys, pg->scale, pg->gs, pg->diag, 1.0 / radius, pg->q2, pg->t2, pg->share);
     k_pg_sum<<<1, 256, 0, pg->s>>>(n, 3, 3, pg->share, pg->red);
     if (pg->m) k_pg_cost<<<(unsigned)((pg->m + 127) / 128), 128, 0, pg->s>>>(pg->m, pg->q2, pg->t2, pg->ei, pg->ej, pg->zq, pg->zt, pg->share);
     k_pg_sum<<<1, 256, 0, pg->s>>>(pg->m, 1, 1, pg->share, pg->red + 4);
-    pg->launches += 6;
+    pg->launches += 5;
     int info_h = 0;
     CK(cudaMemcpyAsync(pg->red_host, pg->red, 5 * sizeof(double), cudaMemcpyDeviceToHost, pg->s));
     CK(cudaMemcpyAsync(&info_h, pg->info, sizeof(int), cudaMemcpyDeviceToHost, pg->s));

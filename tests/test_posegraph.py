@@ -134,6 +134,29 @@ def test_full_lm_solve_matches_oracle(stba, n, offsets):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,offsets,parts", [(200, (1, 2, 3, 4), 5), (300, (1,), 7), (400, (1, 3, 8), 6), (131, (1, 2), 3)])
+def test_partitioned_band_solve_is_the_same_solver(stba, monkeypatch, n, offsets, parts):
+    """The partitioned (multi-SM) elimination is exact: forced on small graphs it must reproduce the oracle like the
+    serial ring solver does (interiors of unequal length, first / last partitions without a left / right separator)."""
+    monkeypatch.setenv("STBA_PG_PARTS", str(parts))
+    G = pg.make_graph(n, offsets=offsets)
+    want_q, want_t, want = pg.solve(G["q0"], G["t0"], G["ei"], G["ej"], G["zq"], G["zt"])
+    with stba.posegraph.PoseGraph(G["q0"], G["t0"], G["ei"], G["ej"], G["zq"], G["zt"]) as p:
+        s = p.solve()
+        q, t = p.get_state()
+    monkeypatch.setenv("STBA_PG_SERIAL", "1")
+    monkeypatch.delenv("STBA_PG_PARTS")
+    with stba.posegraph.PoseGraph(G["q0"], G["t0"], G["ei"], G["ej"], G["zq"], G["zt"]) as p:
+        s1 = p.solve()
+        q1, t1 = p.get_state()
+    assert s.termination_type == want.termination_type and len(s.iterations) == len(want.iterations) == len(s1.iterations)
+    assert np.allclose([i["cost"] for i in s.iterations], [i["cost"] for i in want.iterations], rtol=1e-8)
+    assert np.max(np.abs(q - want_q)) < 1e-7 and np.max(np.abs(t - want_t)) < 1e-7
+    assert np.max(np.abs(q - q1)) < 1e-9 and np.max(np.abs(t - t1)) < 1e-9
+    assert s.gpu_launches > s1.gpu_launches          # six launches per solve instead of one
+
+
+@pytest.mark.gpu
 def test_reference_track_fixture(stba, st4):
     with stba.posegraph.PoseGraph(st4["q0"], st4["t0"], st4["ei"], st4["ej"], st4["zq"], st4["zt"]) as p:
         s = p.solve()
