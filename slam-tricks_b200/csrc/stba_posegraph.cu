@@ -15,8 +15,9 @@
 //   k_pg_band_solve  block-banded Cholesky + both substitutions in ONE CTA: a ring of B + 3 block columns
 //                    lives in shared memory, the next column streams in with cp.async two steps ahead, the
 //                    factor streams out; per column: 6 x 6 Cholesky + inverse, B block solves, B(B+1)/2
-//                    block updates.  Sequential over the columns by nature — round 1 keeps it on one SM
-//                    (≈ 1000 cycles per column); the partitioned (SPIKE-style) version is the round-2 item.
+//                    block updates.  Sequential over the columns by nature: used for short graphs and for the
+//                    reduced separator system of the partitioned solve (k_pg_part_*, further down), which
+//                    factorises ~sqrt(N / B) interiors side by side on as many SMs.
 //   k_pg_update / k_pg_cost / k_pg_gradnorm / k_pg_sum   step, candidate cost, norms (fixed-order sums)
 #include <cuda_runtime.h>
 #include <math.h>
