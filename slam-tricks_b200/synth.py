@@ -294,3 +294,92 @@ CONFIGS = {
     "B": (50, 5000, 50000),            # BASELINE.json configs[1]
     "C": (1000, 100000, 1000000),      # BASELINE.json configs[2]
 }
+
+
+# ------------------------------------------------------------------------------------------------
+# SE(3) pose-graph scenes (BASELINE.json configs[4]).  Restates the shape of the reference's
+# pose-chain simulator (st4-kalman/src/src/pose_simulation.cpp:17-88: a spiral on the sphere of radius 1 around
+# (0,0,1), odometry that drifts) deterministically; same numbers as oracle/pg_oracle.py make_graph for the same
+# seed (tests/test_posegraph.py checks that), but self-contained: product code never imports the oracle.
+# ------------------------------------------------------------------------------------------------
+def _qmul(a, b):
+    ax, ay, az, aw = np.moveaxis(a, -1, 0)
+    bx, by, bz, bw = np.moveaxis(b, -1, 0)
+    return np.stack([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                     aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz], axis=-1)
+
+
+def _qnorm(q):
+    return q / np.linalg.norm(q, axis=-1, keepdims=True)
+
+
+def _qrotate(q, v):
+    return np.einsum("...ij,...j->...i", _rot_from_quat(q), v)
+
+
+def _se3_compose(qa, ta, qb, tb):
+    return _qnorm(_qmul(qa, qb)), ta + _qrotate(qa, tb)
+
+
+def _se3_inverse(q, t):
+    qi = q * np.array([-1.0, -1.0, -1.0, 1.0])
+    return qi, -_qrotate(qi, t)
+
+
+def _se3_exp(xi):
+    """Sophus::SE3d::exp, tangent order [rho, theta] -> (q xyzw, t)."""
+    rho, om = xi[..., :3], xi[..., 3:]
+    th2 = np.sum(om * om, axis=-1)
+    small = th2 < 1e-20
+    th = np.sqrt(np.where(small, 1.0, th2))
+    imag = np.where(small, 0.5 - th2 / 48.0 + th2 * th2 / 3840.0, np.sin(0.5 * th) / th)
+    real = np.where(small, 1.0 - th2 / 8.0 + th2 * th2 / 384.0, np.cos(0.5 * th))
+    q = np.concatenate([imag[..., None] * om, real[..., None]], axis=-1)
+    theta = np.linalg.norm(om, axis=-1)
+    sm = theta < 1e-10
+    tt = np.where(sm, 1.0, theta)
+    a = np.where(sm, 0.5, (1 - np.cos(tt)) / tt ** 2)
+    b = np.where(sm, 1.0 / 6.0, (tt - np.sin(tt)) / tt ** 3)
+    c1 = np.cross(om, rho)
+    c2 = np.cross(om, c1)
+    return q, rho + a[..., None] * c1 + b[..., None] * c2
+
+
+def _relative(q, t, ei, ej):
+    qi, ti = _se3_inverse(q[ei], t[ei])
+    return _se3_compose(qi, ti, q[ej], t[ej])
+
+
+def pose_graph(n=200, offsets=(1, 2, 3, 4), sigma_t=0.01, sigma_r=0.005, drift_t=0.02, drift_r=0.01, seed=20221108, turns=10.0):
+    """Returns dict(q0, t0, ei, ej, zq, zt, q_truth, t_truth): truth = spiral, measurements = noisy relative poses on
+    a band of index offsets (edges sorted by (i, j)), initial guess = integration of noisier (i, i+1) steps."""
+    rng = np.random.default_rng(seed)
+    s = np.arange(n) / max(n - 1, 1)
+    z = 2.0 * s
+    r = np.sqrt(np.maximum(1.0 - (z - 1.0) ** 2, 1e-6))
+    th = 2 * np.pi * turns * s
+    pos = np.stack([r * np.cos(th), r * np.sin(th), z], axis=-1)
+    zc = np.array([0.0, 0.0, 1.0]) - pos
+    zc /= np.linalg.norm(zc, axis=-1, keepdims=True)
+    xa = np.stack([-np.sin(th), np.cos(th), np.zeros(n)], axis=-1)
+    xa -= np.sum(xa * zc, axis=-1, keepdims=True) * zc
+    xa /= np.linalg.norm(xa, axis=-1, keepdims=True)
+    ya = np.cross(zc, xa)
+    qT, tT = _quat_from_rot(np.stack([xa, ya, zc], axis=-1)), pos
+    ei = np.concatenate([np.arange(0, n - o) for o in offsets]).astype(np.int32)
+    ej = np.concatenate([np.arange(o, n) for o in offsets]).astype(np.int32)
+    order = np.lexsort((ej, ei))
+    ei, ej = ei[order], ej[order]
+
+    def measure(a, b, st, sr):
+        zq, zt = _relative(qT, tT, a, b)
+        noise = np.concatenate([rng.normal(0, st, (len(a), 3)), rng.normal(0, sr, (len(a), 3))], axis=1)
+        return _se3_compose(zq, zt, *_se3_exp(noise))
+
+    zq, zt = measure(ei, ej, sigma_t, sigma_r)
+    sq, st = measure(np.arange(n - 1), np.arange(1, n), drift_t, drift_r)
+    q0, t0 = np.zeros((n, 4)), np.zeros((n, 3))
+    q0[0], t0[0] = qT[0], tT[0]
+    for i in range(1, n):
+        q0[i], t0[i] = _se3_compose(q0[i - 1], t0[i - 1], sq[i - 1], st[i - 1])
+    return dict(q0=q0, t0=t0, ei=ei, ej=ej, zq=zq, zt=zt, q_truth=qT, t_truth=tT)

@@ -77,6 +77,13 @@ def test_oracle_reduces_the_drift_of_the_reference_track(st4):
     assert pg.ate(st4["q_truth"], st4["t_truth"], q, t) < 0.02 < 0.4 < pg.ate(st4["q_truth"], st4["t_truth"], st4["q0"], st4["t0"])
 
 
+def test_product_side_generator_equals_the_oracles(stba):
+    # slam-tricks_b200/synth.py pose_graph is self-contained (product code never imports oracle/) and bit-identical
+    for n, off in ((120, (1, 2, 3, 4)), (90, (1, 7, 16))):
+        a, b = stba.synth.pose_graph(n, offsets=off), pg.make_graph(n, offsets=off)
+        assert all(np.array_equal(a[k], b[k]) for k in b)
+
+
 def test_trajectory_csv_round_trip(stba, st4, tmp_path):
     p = str(tmp_path / "truth.csv")
     stba.posegraph.write_trajectory_csv(p, st4["q_truth"], st4["t_truth"])
