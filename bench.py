@@ -305,7 +305,7 @@ def main():
         _, its, _, _, tri_ms = stba.front.triangulate(d["cam_q"], d["cam_t"], d["lm"], d["obs_cam"], d["obs_lm"], d["obs_uv"])
         t3 = time.perf_counter()
         extra["front"] = {"visibility": {"pairs_tested": n_cam * n_lm_total, "visible": int(len(vis["obs_cam"])), "e2e_ms": 1e3 * (t2 - t1),
-                                         "note": "stba_visibility: predicate + ordered compaction, host buffers in and out; the time is dominated by the device-to-host copy of the lists (28 B per visible pair into pageable memory), the three kernels take < 2 ms"},
+                                         "note": "stba_visibility: predicate + ordered compaction, host buffers in and out; the time is dominated by the device-to-host copy of the lists (28 B per visible pair into pageable memory); the kernels take 3.8 ms in total (ncu: profiles/r1_launches_front.md)"},
                           "triangulate": {"landmarks": n_lm_total, "observations": n_obs_total, "kernel_ms": tri_ms, "e2e_ms": 1e3 * (t3 - t2),
                                           "mean_lm_iterations": float(its.mean())}}
     if rank == 0:
