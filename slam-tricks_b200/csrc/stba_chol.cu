@@ -188,7 +188,7 @@ k_gemm_nt(double* __restrict__ S, int lda, int n_rows, int n_cols, int k0, int K
 // are no longer on the critical path.
 #ifdef STBA_CHOL_TIMING
 __device__ long long g_trsm_clk[16];
-#define TTICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_trsm_clk[i] = clock64(); } while (0)
+#define TTICK(i) do { if (threadIdx.x == 0 && blockIdx.x == (gridDim.x > 100 ? 1 : 0)) g_trsm_clk[i] = clock64(); } while (0)
 #else
 #define TTICK(i) do {} while (0)
 #endif
@@ -196,13 +196,15 @@ constexpr int TS_THREADS = 256;
 constexpr int TS_ROWS = 64;
 constexpr int TS_SMEM = (NB * LDS + 8 * NB * 8) * (int)sizeof(double);
 
-__global__ void __launch_bounds__(TS_THREADS, 1)
-k_trsm_sub(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int row0, const double* __restrict__ Linv) {
-  extern __shared__ __align__(16) double smem[];
+// Device-function form: the first 8 warps of the CTA own the 64 rows i0 .. i0 + 63; every warp of the CTA
+// (n_warps of them) helps with the operand loads and must take part in the CTA-wide barriers.  All global
+// reads bypass L1 (cp.async.cg / ld.cg): inside the persistent DAG kernel the operands were written by
+// other SMs during the same launch.
+__device__ __forceinline__ void trsm64_dev(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int i0,
+                                           const double* __restrict__ Linv, double* smem, int n_warps) {
   double* Ls = smem;                         // Ls[c * LDS + r]: L(r, c) below the diagonal blocks, Inv(r, c) inside them
   double* Xs = smem + NB * LDS;              // Xs[warp][col][8 rows]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-  const int i0 = row0 + (int)blockIdx.x * TS_ROWS;
   TTICK(0);
   // Operands arrive in four cp.async groups, one per 32-column block b: the columns 32b..32b+31 of
   // the factor block (Inv_bb inside the diagonal block, L below it) and of the CTA's 64 rows.  Step
@@ -210,7 +212,7 @@ k_trsm_sub(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int row0,
   // column, lanes along the rows: the index arithmetic is warp-uniform and cheap.
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
-    for (int c = 32 * b + warp; c < 32 * b + 32; c += TS_THREADS / 32) {
+    for (int c = 32 * b + warp; c < 32 * b + 32; c += n_warps) {
       double* dl = Ls + c * LDS;
       const bool col_ok = c < nb;
       // rows 32b .. 127 of column c, as pairs (r2, r2 + 1)
@@ -219,9 +221,9 @@ k_trsm_sub(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int row0,
         const double* src = in_diag ? Linv + (size_t)c * NB + r2 : S + (size_t)(k0 + c) * ld + k0 + r2;
         if (col_ok && r2 >= c && r2 + 1 < nb) {
           cp_async16(dl + r2, src, true);
-        } else {                       // diagonal / padding pairs: asynchronous too, so that no lane ever blocks its warp on a load
-          if (col_ok && r2 >= c && r2 < nb) cp_async8(dl + r2, src); else dl[r2] = 0.0;
-          if (col_ok && r2 + 1 >= c && r2 + 1 < nb) cp_async8(dl + r2 + 1, src + 1); else dl[r2 + 1] = 0.0;
+        } else {                       // diagonal / padding pairs (8-byte cp.async is .ca only: it could read a stale L1 line)
+          dl[r2] = (col_ok && r2 >= c && r2 < nb) ? __ldcg(src) : 0.0;
+          dl[r2 + 1] = (col_ok && r2 + 1 >= c && r2 + 1 < nb) ? __ldcg(src + 1) : 0.0;
         }
       }
       // the CTA's 64 rows of panel column c
@@ -231,14 +233,14 @@ k_trsm_sub(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int row0,
         if (col_ok && row + 1 < n_rows) {
           cp_async16(dst, S + (size_t)(k0 + c) * ld + row, true);
         } else {
-          if (col_ok && row < n_rows) cp_async8(dst, S + (size_t)(k0 + c) * ld + row); else dst[0] = 0.0;
+          dst[0] = (col_ok && row < n_rows) ? __ldcg(S + (size_t)(k0 + c) * ld + row) : 0.0;
           dst[1] = 0.0;
         }
       }
     }
     cp_async_commit();
   }
-  double* Xw = Xs + warp * NB * 8;
+  double* Xw = Xs + (warp & 7) * NB * 8;
   const int row = i0 + warp * 8 + g;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -246,6 +248,7 @@ k_trsm_sub(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int row0,
     if (j == 0) cp_async_wait<3>(); else if (j == 1) cp_async_wait<2>(); else if (j == 2) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
     TTICK(2 + 2 * j);
+    if (warp >= 8) continue;
     double acc[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -285,6 +288,12 @@ k_trsm_sub(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int row0,
   TTICK(9);
 }
 
+__global__ void __launch_bounds__(TS_THREADS, 1)
+k_trsm_sub(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int row0, const double* __restrict__ Linv) {
+  extern __shared__ __align__(16) double smem[];
+  trsm64_dev(S, ld, n_rows, k0, nb, row0 + (int)blockIdx.x * TS_ROWS, Linv, smem, TS_THREADS / 32);
+}
+
 // ---- diagonal block: Cholesky + inverse of the factor, one CTA of 512 threads -----------------
 constexpr int PT = 512;          // threads of the diagonal-block kernel
 constexpr int PLD = NB + 1;      // odd leading dimension: column reads by consecutive lanes conflict-free
@@ -298,9 +307,8 @@ __device__ long long g_potrf_clk[64];
 #define TICK(i) do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(PT, 1)
-k_potrf128(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv, int* __restrict__ info) {
-  extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void potrf128_dev(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv,
+                                             int* __restrict__ info, double* sm) {
   double* D = sm;                 // D[c * PLD + r]: lower triangle + diagonal = the factor L;
                                   // strict upper triangle = the inverse, transposed: X(r,c), r > c, at D[r * PLD + c]
   double* xd = sm + NB * PLD;     // diagonal of the inverse
@@ -309,7 +317,7 @@ k_potrf128(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ 
   TICK(0);
   for (int e = tid; e < NB * NB; e += PT) {
     const int r = e % NB, c = e / NB;
-    D[c * PLD + r] = (r < nb && c < nb && r >= c) ? S[(size_t)(k0 + c) * ld + k0 + r] : (r == c ? 1.0 : 0.0);
+    D[c * PLD + r] = (r < nb && c < nb && r >= c) ? __ldcg(S + (size_t)(k0 + c) * ld + k0 + r) : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();
   TICK(1);
@@ -432,25 +440,30 @@ k_potrf128(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ 
   TICK(16);
 }
 
+__global__ void __launch_bounds__(PT, 1)
+k_potrf128(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  potrf128_dev(S, ld, k0, nb, Linv, info, sm);
+}
+
 // Completes Linv_kk: off-diagonal 32 x 32 blocks X_ib = -X_ii (sum_{p=b}^{i-1} L_ip X_pb), from the
 // factor (in S) and the diagonal inverse blocks k_potrf128 stored.  One CTA; runs concurrently with
 // the panel solve / trailing update of the same step.
-__global__ void __launch_bounds__(PT, 1)
-k_inv_offdiag(const double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv) {
-  extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void inv_offdiag_dev(const double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv,
+                                                double* sm) {
   double* D = sm;
   double* xd = sm + NB * PLD;
   double* Tm = xd + NB;
   const int tid = threadIdx.x;
   for (int e = tid; e < NB * NB; e += PT) {
     const int r = e % NB, c = e / NB;
-    if (r >= c) D[c * PLD + r] = (r < nb && c < nb) ? S[(size_t)(k0 + c) * ld + k0 + r] : (r == c ? 1.0 : 0.0);
+    if (r >= c) D[c * PLD + r] = (r < nb && c < nb) ? __ldcg(S + (size_t)(k0 + c) * ld + k0 + r) : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();       // (lower part written before the upper slots of the same columns are filled)
   for (int e = tid; e < NB * 32; e += PT) {
     const int c = e / 32, r = (c & ~31) + (e % 32);
     if (r < c) continue;
-    const double v = Linv[(size_t)c * NB + r];
+    const double v = __ldcg(Linv + (size_t)c * NB + r);
     if (r == c) xd[r] = v; else D[r * PLD + c] = v;
   }
   __syncthreads();
@@ -506,6 +519,12 @@ k_inv_offdiag(const double* __restrict__ S, int ld, int k0, int nb, double* __re
   }
 }
 
+__global__ void __launch_bounds__(PT, 1)
+k_inv_offdiag(const double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv) {
+  extern __shared__ __align__(16) double sm[];
+  inv_offdiag_dev(S, ld, k0, nb, Linv, sm);
+}
+
 // ---- backward substitution, ONE launch --------------------------------------------------------
 // x = L^-T y by 128-blocks.  CTA j owns block j: it keeps y_j in shared memory, applies
 // y_j -= L_kj^T x_k for k = T-1 ... j+1 as each x_k is published (flag in global memory), then
@@ -528,14 +547,14 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 
 __global__ void __launch_bounds__(TBA_THREADS, 1)
 k_trsv_bwd_all(const double* __restrict__ S, int ld, int n, int T, const double* __restrict__ Linv, const double* __restrict__ y,
-               double* x, int* flags, int* __restrict__ info) {
+               double* x, int* flags, int* __restrict__ info, int blk0) {
   extern __shared__ __align__(16) double sm[];
   double* Lb = sm;                          // Lb[c * NB + r] = L(k0 + r, j0 + c)
   double* U = Lb + NB * NB;                 // U[c (c + 1) / 2 + r] = Linv_jj(c, r), r <= c
   double* yj = U + NB * (NB + 1) / 2;
   double* xk = yj + NB;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int j = T - 1 - (int)blockIdx.x, j0 = j * NB;
+  const int j = T - 1 - (blk0 + (int)blockIdx.x), j0 = j * NB;
   const double* Li = Linv + (size_t)j * NB * NB;     // column-major: Linv(c, r) at Li[r * NB + c]
   for (int e = t; e < NB * (NB + 1) / 2; e += TBA_THREADS) {
     int c = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
@@ -697,14 +716,14 @@ k_inv128(const double* __restrict__ S, int ld, int n, double* __restrict__ LinvA
 // shared memory, applies b_j -= L_jk y_k for k = 0 .. j-1 as each y_k is published, then y_j = Linv_jj b_j.
 __global__ void __launch_bounds__(TBA_THREADS, 1)
 k_trsv_fwd_all(const double* __restrict__ S, int ld, int n, int T, const double* __restrict__ Linv, const double* __restrict__ b,
-               double* y, int* flags, int* __restrict__ info) {
+               double* y, int* flags, int* __restrict__ info, int blk0) {
   extern __shared__ __align__(16) double sm[];
   double* Lb = sm;                          // Lb[c * NB + r] = L(j0 + r, k0 + c)
   double* U = Lb + NB * NB;                 // U[c * NB - c (c - 1) / 2 + (r - c)] = Linv_jj(r, c), r >= c
   double* bj = U + NB * (NB + 1) / 2;
   double* yk = bj + NB;
   const int t = threadIdx.x;
-  const int j = (int)blockIdx.x, j0 = j * NB, nbj = min(NB, n - j0);
+  const int j = blk0 + (int)blockIdx.x, j0 = j * NB, nbj = min(NB, n - j0);
   const double* Li = Linv + (size_t)j * NB * NB;
   for (int c = 0; c < NB; ++c)
     for (int r = c + t; r < NB; r += TBA_THREADS) U[c * NB - c * (c - 1) / 2 + (r - c)] = Li[(size_t)c * NB + r];
@@ -771,6 +790,943 @@ __global__ void k_get_row(const double* __restrict__ S, int ld, int n, double* _
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < n) y[c] = S[(size_t)c * ld + n];
 }
+
+// =================================================================================================
+// DAG-scheduled factorisation: ONE persistent kernel, one CTA per SM, tile tasks with data-flow
+// dependencies published through version counters in global memory (STBA_DENSE_OWN).
+//
+// A right-looking blocked Cholesky launched as a chain of kernels is bound, for the last two thirds of
+// the block columns, by the serial chain  potrf(k) -> panel solve -> update of column k+1 -> potrf(k+1)
+// (~80 us per 128 columns at n = 5988: launch gaps, kernel tails, whole-panel kernels on the chain; see
+// profiles/r1_dense_notes.md).  Here only the tile operations that truly are on the critical path stay on
+// it, on two CTAs that do nothing else and hand each other 32-column block columns as they complete:
+//     CTA 0   potrf of the diagonal block k, as soon as tile (k, k) has received update k - 1
+//             (potrf128_prog_dev: publishes block column b and the inverse of its diagonal block);
+//     CTA 1   solve of tile (k+1, k) and update of tile (k+1, k+1), block column by block column (tu_dev);
+// every other SM is a worker pulling tile tasks from three queues by ticket (one atomicAdd), polling the
+// inputs of the tasks it holds:
+//     high priority  64-row panel solves below tile row k+1, each followed on the same worker by the
+//                    64-row update of its rows in block column k+1;
+//     urgent         single-panel 128 x 128 updates of block columns k+2 .. k+1+W, nearest the diagonal first,
+//                    and the partial chunks of a column entering that window;
+//     far            the rest of the trailing matrix, G block columns per update (K = 128 G: one C-tile round
+//                    trip per G panels), plus the completion of the diagonal inverses for the backward solve.
+// No kernel boundaries, no tails; the C tile of a held ticket is prefetched into L2 while the previous task
+// runs and staged through shared memory by TMA bulk copies.
+//
+// Versions: ver[h][j] counts the block-column updates applied to the 64-row half-tile h of block column j;
+// j + 1 means "final" (panel solve done).  pdone[k] = 1: L_kk and its diagonal inverse blocks are in memory;
+// pb[k] / pinv[k]: block columns / inverse blocks of panel k published so far.  Every counter has a single
+// writer at any time (updates of one tile are serialised by the version itself), so publication is a release
+// store after a __threadfence; consumers poll with relaxed loads and fence (or re-load with acquire) once.
+// All operand reads bypass L1 (cp.async.cg / ld.cg / bulk copies): they were written by other SMs during the
+// same launch.  Measured history and the per-CTA cycle / globaltimer profiles: profiles/r2_dense_notes.md.
+// =================================================================================================
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(P, k, slot) do { if ((P).trace && threadIdx.x == 0) (P).trace[(size_t)(k) * 16 + (slot)] = gtime(); } while (0)
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- progressive diagonal-block factorisation (DAG kernel, CTA 0) ---------------------------------
+// Same arithmetic as potrf128_dev, reorganised around the pivot chain, which is what bounds the whole
+// factorisation once the trailing update runs concurrently:
+//   * warp 0 factors the 32 x 32 sub-block with the NEXT column published before the rest of the rank-1
+//     update (the remaining FMAs leave the chain) and the pivot's reciprocal from rcp + Newton (the
+//     reciprocal square root that scales the column is computed beside the chain, not on it);
+//   * the rank-32 update of the rest of the block runs on the FP64 tensor pipe (warps 0..13);
+//   * warp 14 copies every finished 32-column block column to global memory and publishes it (pb), warp 15
+//     inverts the 32 x 32 diagonal factor blocks as they appear and publishes them (pinv): the consumers of
+//     the panel (the solve of the next tile row) start on block column b while b + 1 is being factored.
+constexpr int QLD = NB + 4;      // (q QLD + g) mod 16 distinct over a half-warp: conflict-free DMMA fragments
+constexpr int PROG_SMEM = (NB * QLD + NB + 64) * (int)sizeof(double);
+
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 480;" ::: "memory"); }
+
+// 1 / d: hardware seed (~2^-22) and ONE cubically convergent correction y (1 + e + e^2), e = 1 - d y:
+// three dependent FP64 operations instead of the four of two Newton steps (error e^3 ~ 2^-66).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-d, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+
+__device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv,
+                                                  int* __restrict__ info, double* sm, int* pb_flag, int* pinv_flag,
+                                                  volatile int* s_sig) {
+  double* D = sm;                  // D[c * QLD + r], lower triangle
+  double* xd = sm + NB * QLD;      // 1 / L_jj
+  double* cb = xd + NB;            // 2 x 32 column exchange buffers of the pivot warp
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  TICK(0);
+  // ---- load the lower triangle (16-byte coalesced), identity outside the matrix ----
+  {
+    double2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int e = tid + i * 512;
+      const int c = e >> 6, r2 = (e & 63) * 2;
+      v[i] = (c < nb && r2 < nb && r2 + 1 >= c) ? __ldcg(reinterpret_cast<const double2*>(S + (size_t)(k0 + c) * ld + k0 + r2)) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int e = tid + i * 512;
+      const int c = e >> 6, r2 = (e & 63) * 2;
+      double x0 = v[i].x, x1 = v[i].y;
+      if (!(r2 < nb && c < nb)) x0 = (r2 == c) ? 1.0 : 0.0;
+      if (!(r2 + 1 < nb && c < nb)) x1 = (r2 + 1 == c) ? 1.0 : 0.0;
+      D[c * QLD + r2] = x0;
+      D[c * QLD + r2 + 1] = x1;
+    }
+  }
+  if (tid == 0) *s_sig = 0;
+  __syncthreads();
+  TICK(1);
+  if (warp == 15) {
+    // ---- inverse of the 32 x 32 diagonal factor blocks, as they are produced ----
+    for (int b = 0; b < 4; ++b) {
+      const int b0 = 32 * b;
+      while (*s_sig < b + 1) { }
+      __syncwarp();
+      double x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int p = 0; p < i; ++p) {
+          const double lip = D[(b0 + p) * QLD + b0 + i];
+          if (p & 1) s1 = fma(-lip, x[p], s1); else s0 = fma(-lip, x[p], s0);
+        }
+        x[i] = (s0 + s1) * xd[b0 + i];
+      }
+      const int c = b0 + lane;
+      if (c < nb) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i >= lane && b0 + i < nb) Linv[(size_t)c * NB + b0 + i] = x[i];     // x[lane] = 1 / L_cc
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_gpu(pinv_flag, b + 1);
+    }
+  } else {
+    for (int b = 0; b < 4; ++b) {
+      const int b0 = 32 * b;
+      if (warp == 0) {
+        // (1) pivot chain: lane = row; column j is exchanged through shared memory (shuffles in this
+        //     warp-specialised branch compile to WARPSYNC.COLLECTIVE sequences)
+        double a[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? D[(b0 + c) * QLD + b0 + lane] : 0.0;
+        bool bad = false;
+        cb[lane] = a[0];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const double* col = cb + (j & 1) * 32;
+          const double d = col[j];
+          if (!(d > 0.0) && !bad) { bad = true; if (lane == 0 && b0 + j < nb) atomicCAS(info, 0, k0 + b0 + j + 1); }
+          const double u = (j + 1 < 32) ? a[j] * col[j + 1] : 0.0;   // beside the reciprocal chain
+          const double r = fast_rcp(d);
+          if (j + 1 < 32) {
+            a[j + 1] = fma(-u, r, a[j + 1]);             // one dependent operation after 1 / d
+            cb[((j + 1) & 1) * 32 + lane] = a[j + 1];   // next column out before the rest of the update
+          }
+          const double t = a[j] * r;                     // a_ij / d_j
+#pragma unroll
+          for (int k = j + 2; k < 32; ++k) a[k] = fma(-t, col[k], a[k]);
+          const double rs = fast_rsqrt(d);               // beside the chain: scales column j
+          a[j] = (lane == j) ? d * rs : a[j] * rs;
+          if (lane == j) xd[b0 + j] = rs;
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c <= lane) D[(b0 + c) * QLD + b0 + lane] = a[c];
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *s_sig = b + 1;
+        TICK(20 + b);
+      }
+      bar_workers();
+      TICK(2 + 3 * b);
+      // (2) rows below the sub-block: x L_bb^T = a by forward substitution, one thread per row
+      const int below = NB - b0 - 32;
+      if (tid < below) {
+        const int r = b0 + 32 + tid;
+        double sr[32];
+#pragma unroll
+        for (int p = 0; p < 32; ++p) sr[p] = D[(b0 + p) * QLD + r];
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+          const double x = sr[p] * xd[b0 + p];
+          sr[p] = x;
+          const double* lp = D + (b0 + p) * QLD + b0;
+#pragma unroll
+          for (int c = p + 1; c < 32; ++c) sr[c] = fma(-x, lp[c], sr[c]);
+        }
+#pragma unroll
+        for (int p = 0; p < 32; ++p) D[(b0 + p) * QLD + r] = sr[p];
+      }
+      bar_workers();
+      TICK(3 + 3 * b);
+      if (warp == 14) {
+        // block column b is final: copy it out and publish it
+        for (int c = b0; c < b0 + 32 && c < nb; ++c) {
+          double* dst = S + (size_t)(k0 + c) * ld + k0;
+          const double* srcc = D + c * QLD;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = b0 + lane + 32 * i;
+            if (r >= c && r < nb) dst[r] = srcc[r];
+          }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(pb_flag, b + 1);
+      } else if (below > 0) {
+        // (3) rank-32 update of the remaining lower triangle on the FP64 tensor pipe: 8 x 8 tiles over warps 0..13
+        // 16 x 16 macro tiles (four independent accumulator pairs hide the DMMA latency), lower triangle
+        // of the (below / 16)^2 grid dealt round-robin to the 14 warps
+        const int nt = below / 16;
+        int cnt = 0;
+        for (int ti = 0; ti < nt; ++ti)
+          for (int tj = 0; tj <= ti; ++tj, ++cnt) {
+            if (cnt % 14 != warp) continue;
+            const int r0 = b0 + 32 + 16 * ti, c0 = b0 + 32 + 16 * tj;
+            double acc[2][2][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) acc[mi][ni][e] = D[(c0 + 8 * ni + 2 * q + e) * QLD + r0 + 8 * mi + g];
+#pragma unroll
+            for (int kk = 0; kk < 32; kk += 4) {
+              const double* colp = D + (b0 + kk + q) * QLD;
+              const double a0 = -colp[r0 + g], a1 = -colp[r0 + 8 + g];
+              const double bb0 = colp[c0 + g], bb1 = colp[c0 + 8 + g];
+              dmma(acc[0][0][0], acc[0][0][1], a0, bb0);
+              dmma(acc[0][1][0], acc[0][1][1], a0, bb1);
+              dmma(acc[1][0][0], acc[1][0][1], a1, bb0);
+              dmma(acc[1][1][0], acc[1][1][1], a1, bb1);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) D[(c0 + 8 * ni + 2 * q + e) * QLD + r0 + 8 * mi + g] = acc[mi][ni][e];
+          }
+      }
+      bar_workers();
+      TICK(4 + 3 * b);
+    }
+  }
+  TICK(14);
+  __syncthreads();
+  TICK(15);
+  TICK(16);
+}
+
+constexpr int DAG_THREADS = 512;
+constexpr int UPD_STAGES = 4;
+constexpr int UPD_SMEM = UPD_STAGES * KC * (LDS + LDS) * (int)sizeof(double);
+constexpr int TU_SMEM = (16 * NB * 8 + 32 * (132 + 100 + 68 + 36)) * (int)sizeof(double);
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int DAG_SMEM = cmax(cmax(TS_SMEM, POTRF_SMEM), cmax(UPD_SMEM, cmax(TU_SMEM, PROG_SMEM)));
+enum { TASK_EXIT = -1, TASK_TRSM = 0, TASK_UPD = 1, TASK_INV = 2, TASK_UPD64 = 3 };
+enum { F_HP = 0, F_LP = 32, F_ABORT = 64, F_NPAN = 96, F_UR = 128, F_PDONE = 160 };     // queue heads and the abort flag on their own 128-byte lines
+constexpr long long SPIN_LIMIT = 1ll << 21;     // ~ seconds; a broken schedule must never hang the device
+
+struct DagParams {
+  double* S;
+  int ld, n, n_rows, T, Tr, R64;
+  double* Linv;
+  int* info;
+  int* flags;               // [F_HP] [F_LP] [F_ABORT] [F_NPAN] . pdone[T] ver[R64 * T] pb[T] pinv[T]
+  const int4* hp;           // (type, i or half, j, k | n_k << 16): n_k block columns k .. k + n_k - 1 in one update
+  const int4* ur;
+  const int4* lp;
+  int n_hp, n_ur, n_lp;
+  const int* hp_end;        // hp_end[k]: one past the last high-priority task of step k
+  const int* ur_end;        // same for the urgent queue
+  unsigned long long* trace;   // [T][16] globaltimer stamps of the chain CTAs (profiling runs only)
+  long long* prof;          // per CTA: [0] wait cycles [1] potrf [2] trsm [3] upd [4] inv [5] tasks [6] total
+};
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared (SASS UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+constexpr int LDC = NB + 2;      // staged C tile: (2 q LDC + g) mod 16 distinct over a half-warp -> conflict-free fragment reads
+
+// C(i0.., j0..) -= A(i0.., k0..k0+K) A(j0.., k0..k0+K)^T on a 128 x 128 tile, 16 warps (4 x 4), warp tile 32 x 32.
+// Four warps per scheduler keep the FP64 tensor pipe fed through the per-chunk barriers; the accumulators
+// start as the C tile (store-only epilogue).  On a diagonal tile the warps strictly above the diagonal skip
+// the arithmetic.
+template <int MT>
+__device__ __forceinline__ void upd_dev(double* __restrict__ S, int lda, int n_rows, int n_cols, int k0, int K, int i0, int j0,
+                                        double* smem, long long* ph, unsigned long long* cbar, unsigned& cphase) {
+  constexpr int ROWS = 32 * MT;      // 128 (bulk and diagonal tiles) or 64 (the latency-critical updates of block column k + 1)
+  const long long c_start = clock64();
+  double* As = smem;                               // [UPD_STAGES][KC][LDS]
+  double* Bs = smem + UPD_STAGES * KC * LDS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const bool diag = MT == 4 && i0 == j0;
+  // Off-diagonal tile: 4 x 4 warp grid.  Diagonal tile: only the 10 warp tiles on or below the diagonal carry
+  // arithmetic; they go to warps 0..9 so that the four schedulers (warp & 3) get 3, 3, 2, 2 of them instead
+  // of 4, 3, 2, 1 — this tile is on the critical path of the factorisation.
+  int wm = warp >> 2, wn = warp & 3;
+  bool active = true;
+  if (diag) {
+    // warp:            0  1  2  3  4  5  6  7  8  9
+    active = warp < 10;
+    switch (warp) {
+      case 0: wm = 0; wn = 0; break;  case 1: wm = 1; wn = 0; break;  case 2: wm = 1; wn = 1; break;  case 3: wm = 2; wn = 0; break;
+      case 4: wm = 2; wn = 1; break;  case 5: wm = 2; wn = 2; break;  case 6: wm = 3; wn = 0; break;  case 7: wm = 3; wn = 1; break;
+      case 8: wm = 3; wn = 2; break;  case 9: wm = 3; wn = 3; break;  default: wm = 0; wn = 0; break;
+    }
+  }
+  const double* Ag = S + (size_t)k0 * lda;
+  // The accumulators start as the C tile.  Loads are unconditional from clamped addresses (entries outside
+  // the matrix are never stored), so nothing consumes a loaded value before the first DMMA.
+  // The accumulators start as the C tile.  It is staged through the (still idle) pipeline buffers by TMA bulk
+  // copies, one 1 KB column each: per-lane 8-byte loads of the fragment layout touch half of four 128-byte
+  // lines per instruction and are throttled by the SM's outstanding-request capacity (~10 k cycles per tile,
+  // measured); the bulk engine streams whole lines.  Entries outside the matrix are never stored.
+  double acc[MT][4][2];
+  {
+    const int ncol = min(NB, n_cols - j0);
+    const unsigned col_bytes = (unsigned)min(ROWS, lda - i0) * 8u;       // lda, i0 even: a multiple of 16
+    if (tid == 0) mbar_expect_tx(cbar, col_bytes * (unsigned)ncol);
+    __syncthreads();
+    if (tid < ncol) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy writes to these bytes
+      bulk_g2s(smem + tid * LDC, S + (size_t)(j0 + tid) * lda + i0, col_bytes, cbar);
+    }
+    mbar_wait(cbar, cphase & 1);
+    ++cphase;
+    if (active) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) acc[mt][nt][e] = smem[(wn * 32 + nt * 8 + 2 * q + e) * LDC + wm * (8 * MT) + mt * 8 + g];
+    }
+    __syncthreads();      // every fragment is in registers before the pipeline stages overwrite the tile
+  }
+  const int n_chunks = (K + KC - 1) / KC;
+  auto load_stage = [&](int chunk, int stage) {
+    double* as = As + stage * KC * LDS;
+    double* bs = Bs + stage * KC * LDS;
+#pragma unroll
+    for (int p = 0; p < KC * 64 / DAG_THREADS; ++p) {
+      const int piece = tid + p * DAG_THREADS;
+      const int kk = piece >> 6, r2 = (piece & 63) * 2;
+      const int k = chunk * KC + kk;
+      const bool kin = k < K;
+      const int ra = i0 + r2, rb = j0 + r2;
+      if (r2 < ROWS) cp_async16(as + kk * LDS + r2, Ag + (size_t)(kin ? k : 0) * lda + (ra < n_rows ? ra : 0), kin && ra < n_rows);
+      if (!diag) cp_async16(bs + kk * LDS + r2, Ag + (size_t)(kin ? k : 0) * lda + (rb < n_rows ? rb : 0), kin && rb < n_rows);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < UPD_STAGES - 1; ++s) {
+    if (s < n_chunks) load_stage(s, s);
+    cp_async_commit();
+  }
+  const long long c_issue = clock64();
+  long long c_first = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    cp_async_wait<UPD_STAGES - 2>();
+    __syncthreads();
+    if (c == 0) c_first = clock64();
+    if (c + UPD_STAGES - 1 < n_chunks) load_stage(c + UPD_STAGES - 1, (c + UPD_STAGES - 1) % UPD_STAGES);
+    cp_async_commit();
+    if (!active) continue;
+    const double* as = As + (c % UPD_STAGES) * KC * LDS + wm * (8 * MT) + g;
+    const double* bs = (diag ? As : Bs) + (c % UPD_STAGES) * KC * LDS + wn * 32 + g;
+#pragma unroll
+    for (int kk = 0; kk < KC; kk += 4) {
+      double a[MT], b[4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) a[mt] = -as[(kk + q) * LDS + mt * 8];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) b[nt] = bs[(kk + q) * LDS + nt * 8];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+  }
+  cp_async_wait<0>();
+  const long long c_loop = clock64();
+  if (active) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r = i0 + wm * (8 * MT) + mt * 8 + g;
+      if (r >= n_rows) continue;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = j0 + wn * 32 + nt * 8 + 2 * q + e;
+          if (c < n_cols) S[(size_t)c * lda + r] = acc[mt][nt][e];
+        }
+    }
+  }
+  __syncthreads();      // the stages are reused by the CTA's next task
+  if (tid == 0) { ph[0] += c_issue - c_start; ph[1] += c_first - c_issue; ph[2] += c_loop - c_first; ph[3] += clock64() - c_loop; }
+}
+
+
+__device__ __forceinline__ bool half_exists(const DagParams& P, int h) { return h * 64 < P.n_rows; }
+
+// thread 0: are the inputs of the task final?  (relaxed polls; the caller fences once after claiming)
+__device__ __forceinline__ bool task_ready(const DagParams& P, int4 t) {
+  const int* pdone = P.flags + F_PDONE;
+  const int* ver = pdone + P.T;
+  const int klo = t.w & 0xffff, k = klo + (t.w >> 16) - 1;      // k: the last block column the task reads
+  if (t.x == TASK_TRSM) return ld_relaxed(pdone + k) != 0 && ld_relaxed(ver + t.y * P.T + k) == k;
+  if (t.x == TASK_INV) return ld_relaxed(pdone + k) != 0;
+  if (t.x == TASK_UPD64) {      // rows of half-tile t.y, block column t.z
+    const int h = t.y, j = t.z;
+    const int a0 = ld_relaxed(ver + h * P.T + k), c0 = ld_relaxed(ver + h * P.T + j);
+    const int b0 = ld_relaxed(ver + (2 * j) * P.T + k), b1 = half_exists(P, 2 * j + 1) ? ld_relaxed(ver + (2 * j + 1) * P.T + k) : k + 1;
+    return a0 == k + 1 && b0 == k + 1 && b1 == k + 1 && c0 == k;
+  }
+  const int i = t.y, j = t.z;
+  const bool i2 = half_exists(P, 2 * i + 1);
+  // L rows of tile i and tile j final for block column k; the C tile has received update k - 1
+  const int a0 = ld_relaxed(ver + (2 * i) * P.T + k), a1 = i2 ? ld_relaxed(ver + (2 * i + 1) * P.T + k) : k + 1;
+  const int b0 = ld_relaxed(ver + (2 * j) * P.T + k), b1 = half_exists(P, 2 * j + 1) ? ld_relaxed(ver + (2 * j + 1) * P.T + k) : k + 1;
+  const int c0 = ld_relaxed(ver + (2 * i) * P.T + j), c1 = i2 ? ld_relaxed(ver + (2 * i + 1) * P.T + j) : klo;
+  return a0 == k + 1 && a1 == k + 1 && b0 == k + 1 && b1 == k + 1 && c0 == klo && c1 == klo;
+}
+
+__device__ __forceinline__ void task_publish(const DagParams& P, int4 t) {
+  int* ver = P.flags + F_PDONE + P.T;
+  const int k = (t.w & 0xffff) + (t.w >> 16) - 1;
+  if (t.x == TASK_TRSM) {
+    st_release_gpu(ver + t.y * P.T + k, k + 1);
+  } else if (t.x == TASK_UPD64) {
+    st_release_gpu(ver + t.y * P.T + t.z, k + 1);
+  } else if (t.x == TASK_UPD) {
+    st_release_gpu(ver + (2 * t.y) * P.T + t.z, k + 1);
+    if (half_exists(P, 2 * t.y + 1)) st_release_gpu(ver + (2 * t.y + 1) * P.T + t.z, k + 1);
+  }
+}
+
+__device__ __forceinline__ void dag_abort(const DagParams& P) {
+  atomicCAS(P.info, 0, -1);
+  st_release_gpu(P.flags + F_ABORT, 1);
+}
+
+// ---- merged solve + update of tile row k + 1 (DAG kernel, CTA 1) ------------------------------------
+// X = A(k+1, k) L_kk^-T by forward substitution over the four 32-column blocks AS CTA 0 PUBLISHES THEM
+// (pb / pinv), each warp carrying 8 of the 128 rows; after every block the rank-32 update of the diagonal
+// tile (k+1, k+1), whose accumulators stay in registers (16 x 16 macro tiles of the lower triangle, 36 of
+// them dealt to the 16 warps, 9 per scheduler).  When CTA 0 finishes block column 3 only the last
+// quarter of the solve and of the update is left: the chain per block column is potrf + ~1/4 (solve +
+// update) instead of potrf + solve + update.
+// Shared memory: the X strips (16 warps x 128 columns x 8 rows) and L_kk as four trapezoidal block columns
+// (rows 32 b .. 127 of columns 32 b .. 32 b + 31, the diagonal block replaced by its inverse).
+__device__ __forceinline__ int tu_lb_off(int b) { return b == 0 ? 0 : b == 1 ? 32 * 132 : b == 2 ? 32 * (132 + 100) : 32 * (132 + 100 + 68); }
+__device__ __forceinline__ int tu_lb_ld(int b) { return 132 - 32 * b; }      // = 4 (mod 16): conflict-free B fragments
+
+// CTA-wide wait on one or two counters (thread 0 polls with relaxed loads; the successful observation is
+// repeated as an acquire load, which is much cheaper than a membar).  Returns the first counter's value, or
+// -1 after an abort.
+__device__ __forceinline__ int tu_wait(const DagParams& P, const int* f0, int v0, const int* f1, int v1, bool ge, int* s_ok, long long* t_wait) {
+  if (threadIdx.x == 0) {
+    const long long c0 = clock64();
+    long long spins = 0;
+    int ok = 0;
+    for (;;) {
+      const int a = ld_relaxed(f0), b = f1 ? ld_relaxed(f1) : v1;
+      if (ge ? (a >= v0 && b >= v1) : (a == v0 && b == v1)) {
+        ok = ld_acquire_gpu(f0);
+        if (f1) ok = min(ok, ld_acquire_gpu(f1));
+        break;
+      }
+      if ((++spins & 255) == 0 && ld_relaxed(P.flags + F_ABORT)) { ok = -1; break; }
+      if (spins > SPIN_LIMIT) { dag_abort(P); ok = -1; break; }
+    }
+    *s_ok = ok;
+    *t_wait += clock64() - c0;
+  }
+  __syncthreads();
+  const int ok = *s_ok;
+  __syncthreads();
+  return ok;
+}
+
+__device__ __forceinline__ bool tu_dev(const DagParams& P, int k, double* sm, int* s_ok, long long* prof) {
+  const int T = P.T, ld = P.ld, n_rows = P.n_rows;
+  double* __restrict__ S = P.S;
+  int* pdone = P.flags + F_PDONE;
+  int* ver = pdone + T;
+  const int* pb = ver + P.R64 * T;
+  const int* pinv = pb + T;
+  const int i = k + 1, r0 = i * NB, k0 = k * NB, nb = min(NB, P.n - k0);
+  const bool has_u1 = i < T;
+  const bool h2 = half_exists(P, 2 * i + 1);
+  const double* Linv = P.Linv + (size_t)k * NB * NB;
+  double* Xs = sm;                        // Xs[(strip * NB + col) * 8 + row_in_strip]
+  double* Lb = sm + 16 * NB * 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  TRACE(P, k, 2);
+
+  // macro tiles of the update: t = mi (mi + 1) / 2 + mj, t = warp, warp + 16, warp + 32
+  int mt_i[3], mt_j[3];
+  bool mt_ok[3];
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    const int t = warp + 16 * s;
+    int mi = 0;
+    while ((mi + 1) * (mi + 2) / 2 <= t) ++mi;
+    mt_i[s] = mi; mt_j[s] = t - mi * (mi + 1) / 2;
+    mt_ok[s] = has_u1 && t < 36;
+  }
+  double acc[3][2][2][2];
+  if (has_u1) {
+    // the diagonal tile (k+1, k+1) received update k - 1 from the bulk queue long ago: its loads fly while
+    // the solve still waits for its own inputs
+    if (tu_wait(P, ver + (2 * i) * T + i, k, h2 ? ver + (2 * i + 1) * T + i : nullptr, k, false, s_ok, prof) < 0) return false;
+    TRACE(P, k, 4);
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = min(r0 + 16 * mt_i[s] + 8 * a + g, n_rows - 1), c = min(r0 + 16 * mt_j[s] + 8 * b + 2 * q + e, P.n - 1);
+            acc[s][a][b][e] = mt_ok[s] ? __ldcg(S + (size_t)c * ld + r) : 0.0;
+          }
+  }
+
+  // inputs of the solve: tile (k+1, k) has received update k - 1
+  if (tu_wait(P, ver + (2 * i) * T + k, k, h2 ? ver + (2 * i + 1) * T + k : nullptr, k, false, s_ok, prof) < 0) return false;
+  TRACE(P, k, 3);
+  const long long c_begin = clock64();
+  for (int c = warp; c < NB; c += 16) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int r2 = 2 * lane + 64 * s, row = r0 + r2;
+      double* dst = Xs + ((r2 >> 3) * NB + c) * 8 + (r2 & 7);
+      const double* src = S + (size_t)(k0 + c) * ld + row;
+      if (c < nb && row + 1 < n_rows) {
+        cp_async16(dst, src, true);
+      } else {
+        dst[0] = (c < nb && row < n_rows) ? __ldcg(src) : 0.0;
+        dst[1] = 0.0;
+      }
+    }
+  }
+  cp_async_commit();
+
+  double* Xw = Xs + warp * NB * 8;
+  const int row = r0 + warp * 8 + g;
+  int loaded = 0;                  // block columns of L_kk already requested
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (loaded <= j) {
+      // block column j of L_kk and its inverse diagonal block are in memory — usually several are by now:
+      // request all of them at once
+      const int avail = tu_wait(P, pb + k, j + 1, pinv + k, j + 1, true, s_ok, prof);
+      if (avail < 0) return false;
+      for (int jb = loaded; jb < min(avail, 4); ++jb) {
+        double* Lj = Lb + tu_lb_off(jb);
+        const int ldj = tu_lb_ld(jb);
+        for (int cl = warp; cl < 32; cl += 16) {
+          const int c = 32 * jb + cl;
+          double* dl = Lj + cl * ldj - 32 * jb;           // dl[r] = L(r, c), r >= 32 jb
+          const bool col_ok = c < nb;
+          for (int r2 = 32 * jb + 2 * lane; r2 < NB; r2 += 64) {
+            const bool in_diag = r2 < 32 * jb + 32;
+            const double* src = in_diag ? Linv + (size_t)c * NB + r2 : S + (size_t)(k0 + c) * ld + k0 + r2;
+            if (col_ok && r2 >= c && r2 + 1 < nb) {
+              cp_async16(dl + r2, src, true);
+            } else {
+              dl[r2] = (col_ok && r2 >= c && r2 < nb) ? __ldcg(src) : 0.0;
+              dl[r2 + 1] = (col_ok && r2 + 1 >= c && r2 + 1 < nb) ? __ldcg(src + 1) : 0.0;
+            }
+          }
+        }
+      }
+      loaded = min(avail, 4);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    TRACE(P, k, 5 + j);
+    {
+      double a4[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) a4[nt][e] = Xw[(32 * j + 8 * nt + 2 * q + e) * 8 + g];
+#pragma unroll
+      for (int p = 0; p < j; ++p) {
+        const double* Lp = Lb + tu_lb_off(p) + (32 * j - 32 * p) + g;
+        const int ldp = tu_lb_ld(p);
+#pragma unroll
+        for (int kk = 0; kk < 32; kk += 4) {
+          const double a = -Xw[(32 * p + kk + q) * 8 + g];
+          const double* bs = Lp + (kk + q) * ldp;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma(a4[nt][0], a4[nt][1], a, bs[nt * 8]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) Xw[(32 * j + 8 * nt + 2 * q + e) * 8 + g] = a4[nt][e];
+      __syncwarp();
+      double out[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+      const double* Ij = Lb + tu_lb_off(j) + g;
+      const int ldj = tu_lb_ld(j);
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+        const double a = Xw[(32 * j + kk + q) * 8 + g];
+        const double* bs = Ij + (kk + q) * ldj;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma(out[nt][0], out[nt][1], a, bs[nt * 8]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 32 * j + 8 * nt + 2 * q + e;
+          Xw[c * 8 + g] = out[nt][e];
+          if (row < n_rows && c < nb) S[(size_t)(k0 + c) * ld + row] = out[nt][e];
+        }
+    }
+    if (j == 3) __threadfence();
+    __syncthreads();
+    if (j == 3 && tid == 0) {      // the tile row is solved: the updates of block column k + 1 may start
+      st_release_gpu(ver + (2 * i) * T + k, k + 1);
+      if (h2) st_release_gpu(ver + (2 * i + 1) * T + k, k + 1);
+      TRACE(P, k, 9);
+    }
+    if (has_u1) {
+      // rank-32 update of the diagonal tile, the (up to) three macro tiles of the warp interleaved: twelve
+      // independent accumulator pairs per k-step
+      const double* xa[3];
+      const double* xb[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        xa[s] = Xs + ((2 * mt_i[s]) * NB + 32 * j + q) * 8 + g;
+        xb[s] = Xs + ((2 * mt_j[s]) * NB + 32 * j + q) * 8 + g;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          if (!mt_ok[s]) continue;
+          const double a0 = -xa[s][kk * 8], a1 = -xa[s][NB * 8 + kk * 8];
+          const double b0 = xb[s][kk * 8], b1 = xb[s][NB * 8 + kk * 8];
+          dmma(acc[s][0][0][0], acc[s][0][0][1], a0, b0);
+          dmma(acc[s][0][1][0], acc[s][0][1][1], a0, b1);
+          dmma(acc[s][1][0][0], acc[s][1][0][1], a1, b0);
+          dmma(acc[s][1][1][0], acc[s][1][1][1], a1, b1);
+        }
+      }
+    }
+  }
+  if (has_u1) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      if (!mt_ok[s]) continue;
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = r0 + 16 * mt_i[s] + 8 * a + g, c = r0 + 16 * mt_j[s] + 8 * b + 2 * q + e;
+            if (r < n_rows && c < P.n) S[(size_t)c * ld + r] = acc[s][a][b][e];
+          }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      st_release_gpu(ver + (2 * i) * T + i, k + 1);
+      if (h2) st_release_gpu(ver + (2 * i + 1) * T + i, k + 1);
+    }
+  }
+  __syncthreads();
+  TRACE(P, k, 10);
+  if (tid == 0) { prof[2] += clock64() - c_begin; prof[5] += 1; }
+  return true;
+}
+
+// Worker scheduling (thread 0).  Tasks are claimed by TICKET (one atomicAdd on the queue head, many in flight)
+// and their inputs are polled afterwards; a worker holds at most one ticket per queue and runs whichever of its
+// two tasks becomes ready first.  Claiming only tasks whose inputs are final — a compare-and-swap on the head
+// after a readiness check — serialises every claim behind ~1.3 us of dependent L2 round trips: 19 000 tasks,
+// 25 ms (measured).  High-priority tickets are only taken inside the steps whose block column is factored
+// (hp_end[npan - 1]), so a worker is never parked on a panel solve of a later step.
+// Deadlock freedom: both queue orders extend to one topological order of the task graph (steps only depend on
+// earlier steps); the first unfinished task in that order has all inputs final and is either on a dedicated
+// CTA, or held by a worker (which polls it), or at the head of its queue with no ticket of that queue
+// outstanding — and workers never block while holding a ticket.
+struct WorkerState {
+  int4 t_hp, t_ur, t_lp;
+  bool have_hp = false, have_ur = false, have_lp = false, hp_done = false, ur_done = false, lp_done = false;
+  bool new_hp = false, new_ur = false, new_lp = false;     // ticket taken since the last prefetch round
+  int patience = 0;        // polls during which only the held high-priority ticket is considered
+};
+
+// All threads: pull the tile a held ticket will read-modify-write (C tile of an update, panel rows of a
+// solve) into L2.  S (287 MB at n = 5988) does not stay in the 126 MB L2 between two updates of a tile; without
+// this every task starts with ~11 k cycles of exposed HBM latency (measured).
+__device__ __forceinline__ void prefetch_task(const DagParams& P, int4 t) {
+  const int tid = threadIdx.x;
+  int r0, c0, nr;
+  if (t.x == TASK_UPD) { r0 = t.y * NB; c0 = t.z * NB; nr = NB; }
+  else if (t.x == TASK_TRSM) { r0 = t.y * 64; c0 = (t.w & 0xffff) * NB; nr = 64; }
+  else if (t.x == TASK_UPD64) { r0 = t.y * 64; c0 = t.z * NB; nr = 64; }
+  else return;
+  const int lines_per_col = nr / 16;                 // 128-byte lines
+  for (int e = tid; e < NB * lines_per_col; e += DAG_THREADS) {
+    const int c = c0 + e / lines_per_col, r = r0 + (e % lines_per_col) * 16;
+    if (c < P.n && r < P.n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.S + (size_t)c * P.ld + r));
+  }
+}
+
+// A ticket of the high-priority / urgent queue is only taken inside the steps whose block column is factored.
+__device__ __forceinline__ void take_gated(const DagParams& P, int flag, const int4* q, int n_q, const int* q_end, int4& t, bool& have,
+                                           bool& done, bool& fresh) {
+  if (have || done) return;
+  const int npan = ld_relaxed(P.flags + F_NPAN), head = ld_relaxed(P.flags + flag);
+  const int limit = npan > 0 ? q_end[npan - 1] : 0;
+  if (head >= n_q) {
+    done = true;
+  } else if (head < limit) {
+    const int h = atomicAdd(P.flags + flag, 1);
+    if (h < n_q) { t = q[h]; have = true; fresh = true; } else done = true;
+  }
+}
+__device__ __forceinline__ void take_far(const DagParams& P, WorkerState& w) {
+  if (w.have_lp || w.lp_done) return;
+  const int l = atomicAdd(P.flags + F_LP, 1);
+  if (l < P.n_lp) { w.t_lp = P.lp[l]; w.have_lp = true; w.new_lp = true; } else w.lp_done = true;
+}
+
+__device__ __forceinline__ int4 next_task(const DagParams& P, WorkerState& w) {
+  long long spins = 0;
+  for (;;) {
+    if ((spins & 63) == 0 && ld_relaxed(P.flags + F_ABORT)) return make_int4(TASK_EXIT, 0, 0, 0);
+    take_gated(P, F_HP, P.hp, P.n_hp, P.hp_end, w.t_hp, w.have_hp, w.hp_done, w.new_hp);
+    if (w.have_hp && task_ready(P, w.t_hp)) { w.have_hp = false; w.new_hp = false; w.patience = 0; __threadfence(); return w.t_hp; }
+    if (w.have_hp && w.patience > 0) {      // the update that follows this worker's panel solve: its last input (the solve of
+      --w.patience;                         // tile row k + 1 on CTA 1) is microseconds away — do not start a long task now
+      ++spins;
+      __nanosleep(100);
+      continue;
+    }
+    take_gated(P, F_UR, P.ur, P.n_ur, P.ur_end, w.t_ur, w.have_ur, w.ur_done, w.new_ur);
+    if (w.have_ur && task_ready(P, w.t_ur)) { w.have_ur = false; w.new_ur = false; __threadfence(); return w.t_ur; }
+    take_far(P, w);
+    if (w.have_lp && task_ready(P, w.t_lp)) { w.have_lp = false; w.new_lp = false; __threadfence(); return w.t_lp; }
+    if (w.hp_done && w.ur_done && w.lp_done && !w.have_hp && !w.have_ur && !w.have_lp) return make_int4(TASK_EXIT, 0, 0, 0);
+    if (++spins > SPIN_LIMIT) { dag_abort(P); return make_int4(TASK_EXIT, 0, 0, 0); }
+    __nanosleep(spins < 8 ? 100 : 400);
+  }
+}
+
+__global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag(const DagParams P) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int4 s_task;
+  __shared__ int s_ok;
+  __shared__ int s_sig;
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const int T = P.T;
+  int* pdone = P.flags + F_PDONE;
+  __shared__ unsigned long long s_cbar;     // completion barrier of the C-tile bulk copies
+  unsigned cphase = 0;                      // uses of s_cbar so far (CTA-uniform)
+  if (threadIdx.x == 0) mbar_init(&s_cbar, 1);
+  __shared__ long long s_prof[16];      // thread 0 only: [0] wait [1] potrf [2] trsm [3] upd [4] inv [5] tasks [6] start
+  if (tid == 0) {
+    for (int i = 0; i < 16; ++i) s_prof[i] = 0;
+    s_prof[6] = clock64();
+  }
+#define t_wait s_prof[0]
+#define t_potrf s_prof[1]
+#define t_trsm s_prof[2]
+#define t_upd s_prof[3]
+#define t_inv s_prof[4]
+#define n_tasks s_prof[5]
+
+  auto run = [&](int4 t) {     // all threads
+    const long long c0 = clock64();
+    const int k = t.w & 0xffff, nk = t.w >> 16, k0 = k * NB, nb = min(NB, P.n - k0);
+    if (t.x == TASK_TRSM) trsm64_dev(P.S, P.ld, P.n_rows, k0, nb, t.y * 64, P.Linv + (size_t)k * NB * NB, sm, DAG_THREADS / 32);
+    else if (t.x == TASK_UPD) upd_dev<4>(P.S, P.ld, P.n_rows, P.n, k0, NB * nk, t.y * NB, t.z * NB, sm, s_prof + 8, &s_cbar, cphase);
+    else if (t.x == TASK_UPD64) upd_dev<2>(P.S, P.ld, P.n_rows, P.n, k0, NB, t.y * 64, t.z * NB, sm, s_prof + 12, &s_cbar, cphase);
+    else if (t.x == TASK_INV) inv_offdiag_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, sm);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      task_publish(P, t);
+      const long long dt = clock64() - c0;
+      if (t.x == TASK_TRSM) t_trsm += dt; else if (t.x == TASK_UPD || t.x == TASK_UPD64) t_upd += dt; else t_inv += dt;
+      ++n_tasks;
+    }
+  };
+  if (b == 0) {
+    // ---- the factorisation chain: diagonal blocks ----
+    for (int k = 0; k < T; ++k) {
+      const int k0 = k * NB, nb = min(NB, P.n - k0);
+      if (tid == 0) {
+        const long long c0 = clock64();
+        const int* ver = pdone + T;
+        long long spins = 0;
+        int ok = 1;
+        for (;;) {
+          const int v0 = ld_relaxed(ver + (2 * k) * T + k), v1 = half_exists(P, 2 * k + 1) ? ld_relaxed(ver + (2 * k + 1) * T + k) : k;
+          if (v0 == k && v1 == k) break;
+          if ((++spins & 255) == 0 && ld_relaxed(P.flags + F_ABORT)) { ok = 0; break; }
+          if (spins > SPIN_LIMIT) { dag_abort(P); ok = 0; break; }
+        }
+        __threadfence();
+        s_ok = ok;
+        t_wait += clock64() - c0;
+      }
+      __syncthreads();
+      const bool ok = s_ok != 0;
+      __syncthreads();
+      if (!ok) break;
+      TRACE(P, k, 0);
+      const long long c0 = clock64();
+      {
+        int* pb = P.flags + F_PDONE + T + P.R64 * T;
+        potrf128_prog_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, P.info, sm, pb + k, pb + T + k, &s_sig);
+      }
+      __threadfence();
+      __syncthreads();
+      TRACE(P, k, 1);
+      if (tid == 0) { st_release_gpu(pdone + k, 1); st_release_gpu(P.flags + F_NPAN, k + 1); t_potrf += clock64() - c0; ++n_tasks; }
+      // the right-hand-side row n lives inside the last diagonal tile when n is not a multiple of 128
+      if (k == T - 1 && P.n_rows > P.n && P.n < T * NB) {
+        trsm64_dev(P.S, P.ld, P.n_rows, k0, nb, P.n, P.Linv + (size_t)k * NB * NB, sm, DAG_THREADS / 32);
+        __syncthreads();
+      }
+    }
+  } else if (b == 1) {
+    // ---- tile row k + 1: solve of tile (k+1, k) and update of tile (k+1, k+1), pipelined with CTA 0 ----
+    for (int k = 0; k < T; ++k) {
+      if (!half_exists(P, 2 * (k + 1))) break;
+      if (!tu_dev(P, k, sm, &s_ok, s_prof)) break;
+    }
+  } else {
+    WorkerState w;
+    __shared__ int4 s_pref[3];
+    for (;;) {
+      if (tid == 0) {
+        const long long c0 = clock64();
+        const int4 t = next_task(P, w);
+        s_task = t;
+        // refill the tickets right away: their tiles are prefetched into L2 while this task runs
+        if (t.x != TASK_EXIT) {
+          take_gated(P, F_UR, P.ur, P.n_ur, P.ur_end, w.t_ur, w.have_ur, w.ur_done, w.new_ur);
+          take_far(P, w);
+        }
+        s_pref[0] = w.new_hp ? w.t_hp : make_int4(TASK_EXIT, 0, 0, 0);
+        s_pref[1] = w.new_lp ? w.t_lp : make_int4(TASK_EXIT, 0, 0, 0);
+        s_pref[2] = w.new_ur ? w.t_ur : make_int4(TASK_EXIT, 0, 0, 0);
+        w.new_hp = w.new_lp = w.new_ur = false;
+        t_wait += clock64() - c0;
+      }
+      __syncthreads();
+      const int4 t = s_task, p0 = s_pref[0], p1 = s_pref[1], p2 = s_pref[2];
+      __syncthreads();
+      if (t.x == TASK_EXIT) break;
+      prefetch_task(P, p0);
+      prefetch_task(P, p1);
+      prefetch_task(P, p2);
+      run(t);
+      // A panel solve is followed on the same worker by the update of its rows in block column k + 1 (held
+      // like a claimed ticket: it never blocks the worker).  The pair is what the chain waits for.
+      if (tid == 0 && t.x == TASK_TRSM && (t.w & 0xffff) + 1 < T && !w.have_hp) {
+        w.t_hp = make_int4(TASK_UPD64, t.y, (t.w & 0xffff) + 1, t.w);
+        w.have_hp = true;
+        w.new_hp = false;
+        w.patience = 64;
+      }
+    }
+  }
+  if (P.prof && tid == 0) {
+    long long* o = P.prof + (size_t)b * 16;
+    for (int i = 0; i < 4; ++i) o[8 + i] = s_prof[8 + i];
+    o[0] = t_wait; o[1] = t_potrf; o[2] = t_trsm; o[3] = t_upd; o[4] = t_inv; o[5] = n_tasks; o[6] = clock64() - s_prof[6];
+  }
+#undef t_wait
+#undef t_potrf
+#undef t_trsm
+#undef t_upd
+#undef t_inv
+#undef n_tasks
+}
+
+// The one-launch substitution kernels spin on flags of CTAs with a smaller block index.  CUDA does not promise
+// in-order dispatch once a grid exceeds the resident capacity, so the grid is cut into launches of at most one
+// CTA per SM: inside a launch every CTA is resident, across launches the producers have already finished.
+static int substitution_chunk() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 1;
+  }
+  return sms;
+}
 #define CKC(call)                                                                                           \
   do {                                                                                                      \
     cudaError_t e_ = (call);                                                                                \
@@ -792,6 +1748,15 @@ struct CholPlan {
   int2* tiles = nullptr;      // device tile lists
   int* flags = nullptr;       // x_k-ready flags of the one-launch backward substitution
   cudaGraphExec_t exec = nullptr;
+  // DAG-scheduled persistent factorisation (default)
+  bool dag = false;
+  int4 *hp = nullptr, *ur = nullptr, *lp = nullptr;
+  int* hp_end = nullptr;
+  int n_hp = 0, n_ur = 0, n_lp = 0, grid = 0, R64 = 0, Tr = 0;
+  int* dflags = nullptr;
+  size_t n_dflags = 0;
+  long long* prof = nullptr;
+  unsigned long long* trace = nullptr;
   cudaStream_t side = nullptr, inv = nullptr;
   std::vector<cudaEvent_t> events;
   int launches = 0;
@@ -807,6 +1772,13 @@ static void destroy_plan(CholPlan* p) {
   if (p->ybuf) cudaFree(p->ybuf);
   if (p->tiles) cudaFree(p->tiles);
   if (p->flags) cudaFree(p->flags);
+  if (p->hp) cudaFree(p->hp);
+  if (p->lp) cudaFree(p->lp);
+  if (p->ur) cudaFree(p->ur);
+  if (p->hp_end) cudaFree(p->hp_end);
+  if (p->dflags) cudaFree(p->dflags);
+  if (p->prof) cudaFree(p->prof);
+  if (p->trace) cudaFree(p->trace);
   if (p->side) cudaStreamDestroy(p->side);
   if (p->inv) cudaStreamDestroy(p->inv);
   for (auto e : p->events) cudaEventDestroy(e);
@@ -889,9 +1861,161 @@ static int enqueue(CholPlan& P, cudaStream_t main, bool lookahead) {
   k_get_row<<<(n + 255) / 256, 256, 0, main>>>(S, ld, n, P.ybuf);
   ++P.launches;
   CKC(cudaMemsetAsync(P.flags, 0, (size_t)T * sizeof(int), main));
-  k_trsv_bwd_all<<<T, TBA_THREADS, TBA_SMEM, main>>>(S, ld, n, T, P.Linv, P.ybuf, P.rhs, P.flags, P.info);
+  for (int b0 = 0; b0 < T; b0 += substitution_chunk())
+    k_trsv_bwd_all<<<std::min(T - b0, substitution_chunk()), TBA_THREADS, TBA_SMEM, main>>>(S, ld, n, T, P.Linv, P.ybuf, P.rhs, P.flags, P.info, b0);
   ++P.launches;
   CKC(cudaGetLastError());
+  return STBA_OK;
+}
+
+// Task queues of the DAG kernel (host, once per plan).  High priority: for every block column k the panel
+// solves of the 64-row halves below tile (k+1, k), then the updates of block column k+1; low priority: the
+// bulk trailing update of step k, block columns ascending (the next panel's column first), then the
+// completion of the diagonal inverse of block k.  Queue order is a topological order of the task graph.
+static int build_dag_plan(CholPlan& P) {
+  const int n = P.n, T = (n + NB - 1) / NB, n_rows = n + 1;
+  P.Tr = (n_rows + NB - 1) / NB;
+  P.R64 = (n_rows + 63) / 64;
+  // Three queues, each in a topological order of the task graph (sorted by the last block column read):
+  //   high priority  step k: panel solves of the 64-row halves below tile row k + 1, then the 64-row updates of
+  //                  block column k + 1 (tile row k + 1 itself belongs to CTA 1);
+  //   urgent         step k: single-panel updates of block columns k + 2 .. k + 1 + W — everything the chain
+  //                  needs from the trailing matrix, so the factorisation runs ahead of the bulk;
+  //   far            block columns beyond the window receive their updates lazily, G block columns at a
+  //                  time (K = 128 G: one C-tile round trip per G updates), the remainder when the column enters
+  //                  the window; plus the completion of the diagonal inverses for the backward substitution.
+  int W = 2, G = 3;
+  if (const char* s = getenv("STBA_CHOL_WINDOW")) W = std::max(1, atoi(s));
+  if (const char* s = getenv("STBA_CHOL_AGG")) G = std::max(1, std::min(16, atoi(s)));
+  auto enc = [](int klo, int nk) { return klo | (nk << 16); };
+  std::vector<int4> hp, ur;
+  std::vector<std::vector<int4>> far_by_level(T);
+  std::vector<int> hp_end(T, 0), ur_end(T, 0);
+  for (int k = 0; k < T; ++k) {
+    // (the update of the same rows in block column k + 1 follows each solve on the same worker)
+    for (int h = 2 * (k + 2); h < P.R64; ++h) hp.push_back(make_int4(TASK_TRSM, h, 0, enc(k, 1)));
+    hp_end[k] = (int)hp.size();
+    // urgent: block column j receives panel k as a single update iff k >= j - 1 - W (and k <= j - 2); tile rows
+    // nearest the diagonal first — those are the ones the chain waits for
+
+    far_by_level[k].push_back(make_int4(TASK_INV, 0, 0, enc(k, 1)));
+  }
+  // far: block column j receives panels 0 .. j - 2 - W in aligned chunks of G, queued at the level of the chunk's last
+  // panel.  The remainder (fewer than G panels, applied when the column enters the window) is URGENT: queued
+  // behind the bulk it would stall the chain for a whole level of far work.
+  std::vector<std::vector<int4>> rem_by_level(T);
+  for (int j = 2; j < T; ++j) {
+    const int last = j - 2 - W;        // last far panel of this block column
+    for (int klo = 0; klo <= last; klo += G) {
+      const int nk = std::min(G, last - klo + 1);
+      auto& dst = (nk == G) ? far_by_level[klo + nk - 1] : rem_by_level[klo + nk - 1];
+      for (int i = j; i < P.Tr; ++i) dst.push_back(make_int4(TASK_UPD, i, j, enc(klo, nk)));
+    }
+  }
+  for (int k = 0; k < T; ++k) {
+    for (int i = k + 2; i < P.Tr; ++i)
+      for (int j = k + 2; j < T && j <= k + 1 + W && j <= i; ++j) ur.push_back(make_int4(TASK_UPD, i, j, enc(k, 1)));
+    ur.insert(ur.end(), rem_by_level[k].begin(), rem_by_level[k].end());    // needed by the urgent updates of step k + 1
+    ur_end[k] = (int)ur.size();
+  }
+  std::vector<int4> lp;
+  for (int k = 0; k < T; ++k) {
+    // within a level: block columns ascending (stable: the chunks were appended column by column), the inverse last
+    std::stable_sort(far_by_level[k].begin(), far_by_level[k].end(), [](const int4& a, const int4& b) {
+      const int ja = a.x == TASK_INV ? (1 << 30) : a.z, jb = b.x == TASK_INV ? (1 << 30) : b.z;
+      return ja < jb;
+    });
+    lp.insert(lp.end(), far_by_level[k].begin(), far_by_level[k].end());
+  }
+  P.n_hp = (int)hp.size();
+  P.n_ur = (int)ur.size();
+  P.n_lp = (int)lp.size();
+  CKC(cudaMalloc(&P.hp, std::max<size_t>(hp.size(), 1) * sizeof(int4)));
+  CKC(cudaMalloc(&P.ur, std::max<size_t>(ur.size(), 1) * sizeof(int4)));
+  CKC(cudaMalloc(&P.lp, std::max<size_t>(lp.size(), 1) * sizeof(int4)));
+  CKC(cudaMemcpy(P.hp, hp.data(), hp.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(P.ur, ur.data(), ur.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(P.lp, lp.data(), lp.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CKC(cudaMalloc(&P.hp_end, 2 * T * sizeof(int)));
+  CKC(cudaMemcpy(P.hp_end, hp_end.data(), T * sizeof(int), cudaMemcpyHostToDevice));
+  CKC(cudaMemcpy(P.hp_end + T, ur_end.data(), T * sizeof(int), cudaMemcpyHostToDevice));
+  P.n_dflags = (size_t)F_PDONE + T + (size_t)P.R64 * T + 2 * (size_t)T;
+  CKC(cudaMalloc(&P.dflags, P.n_dflags * sizeof(int)));
+  int dev = 0, sms = 0;
+  CKC(cudaGetDevice(&dev));
+  CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  P.grid = sms;
+  if (const char* g = getenv("STBA_CHOL_GRID")) P.grid = std::max(3, std::min(sms, atoi(g)));
+  CKC(cudaFuncSetAttribute(k_chol_dag, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM));
+  if (getenv("STBA_CHOL_PROF")) {
+    CKC(cudaMalloc(&P.prof, (size_t)P.grid * 16 * sizeof(long long)));
+    CKC(cudaMemset(P.prof, 0, (size_t)P.grid * 16 * sizeof(long long)));
+    CKC(cudaMalloc(&P.trace, (size_t)T * 16 * sizeof(unsigned long long)));
+    CKC(cudaMemset(P.trace, 0, (size_t)T * 16 * sizeof(unsigned long long)));
+  }
+  return STBA_OK;
+}
+
+static int run_dag(CholPlan& P, cudaStream_t stream) {
+  const int n = P.n, ld = P.ld, T = (n + NB - 1) / NB;
+  k_put_row<<<(n + 255) / 256, 256, 0, stream>>>(P.S, ld, n, P.rhs);
+  CKC(cudaMemsetAsync(P.dflags, 0, P.n_dflags * sizeof(int), stream));
+  DagParams dp;
+  dp.S = P.S; dp.ld = ld; dp.n = n; dp.n_rows = n + 1; dp.T = T; dp.Tr = P.Tr; dp.R64 = P.R64;
+  dp.Linv = P.Linv; dp.info = P.info; dp.flags = P.dflags;
+  dp.hp = P.hp; dp.ur = P.ur; dp.lp = P.lp; dp.n_hp = P.n_hp; dp.n_ur = P.n_ur; dp.n_lp = P.n_lp; dp.hp_end = P.hp_end; dp.ur_end = P.hp_end + T; dp.prof = P.prof; dp.trace = P.trace;
+  void* args[] = {&dp};
+  CKC(cudaLaunchCooperativeKernel((const void*)k_chol_dag, dim3(P.grid), dim3(DAG_THREADS), args, DAG_SMEM, stream));
+  k_get_row<<<(n + 255) / 256, 256, 0, stream>>>(P.S, ld, n, P.ybuf);
+  CKC(cudaMemsetAsync(P.flags, 0, (size_t)T * sizeof(int), stream));
+  for (int b0 = 0; b0 < T; b0 += substitution_chunk())
+    k_trsv_bwd_all<<<std::min(T - b0, substitution_chunk()), TBA_THREADS, TBA_SMEM, stream>>>(P.S, ld, n, T, P.Linv, P.ybuf, P.rhs, P.flags, P.info, b0);
+  CKC(cudaGetLastError());
+  P.launches = 4;
+  if (P.prof) {
+    CKC(cudaStreamSynchronize(stream));
+    std::vector<long long> h((size_t)P.grid * 16);
+    CKC(cudaMemcpy(h.data(), P.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    auto row = [&](int b) {
+      const long long* o = &h[(size_t)b * 16];
+      fprintf(stderr, "[chol dag] cta %3d: wait %8lld potrf %8lld trsm %8lld upd %8lld inv %8lld tasks %5lld total %8lld | upd phases: issue %lld first %lld loop %lld store %lld\n", b, o[0], o[1], o[2], o[3],
+              o[4], o[5], o[6], o[8], o[9], o[10], o[11]);
+    };
+    for (int b = 0; b < std::min(P.grid, 4); ++b) row(b);
+    long long w = 0, tr = 0, up = 0, iv = 0, nt = 0, tot = 0;
+    for (int b = 2; b < P.grid; ++b) { const long long* o = &h[(size_t)b * 16]; w += o[0]; tr += o[2]; up += o[3]; iv += o[4]; nt += o[5]; tot += o[6]; }
+#ifdef STBA_CHOL_TIMING
+    {
+      long long hc[64];
+      cudaMemcpyFromSymbol(hc, g_potrf_clk, sizeof(hc));
+      long long ht[16];
+      cudaMemcpyFromSymbol(ht, g_trsm_clk, sizeof(ht));
+      fprintf(stderr, "[trsm clocks, last call of CTA 0]");
+      for (int i = 1; i <= 9; ++i) fprintf(stderr, " %d:%lld", i, ht[i] - ht[i - 1]);
+      fprintf(stderr, "\n[potrf128 clocks, last panel]");
+      for (int i = 1; i <= 16; ++i) fprintf(stderr, " %d:%lld", i, hc[i] - hc[i - 1]);
+      for (int b = 0; b < 4; ++b) fprintf(stderr, " potf2_%d:%lld", b, hc[20 + b] - hc[b ? 1 + 3 * b : 1]);
+      fprintf(stderr, "\n");
+    }
+#endif
+    if (P.trace) {
+      std::vector<unsigned long long> tr((size_t)T * 16);
+      CKC(cudaMemcpy(tr.data(), P.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      const unsigned long long t0 = tr[0];
+      fprintf(stderr, "[chol trace] us since potrf(0) start: k | P start, P end | TU in, X ready, C ready, step0..3 start, X published, TU end\n");
+      fprintf(stderr, "[chol trace] potrf start times (us):");
+      for (int k = 0; k < T; ++k) fprintf(stderr, " %.0f", (double)(tr[(size_t)k * 16] - t0) * 1e-3);
+      fprintf(stderr, "\n");
+      for (int k = 0; k < T; k += (k < 4 || k + 5 > T) ? 1 : 6) {
+        fprintf(stderr, "[chol trace] %2d |", k);
+        for (int s = 0; s <= 10; ++s) fprintf(stderr, " %8.1f%s", tr[(size_t)k * 16 + s] ? (double)(tr[(size_t)k * 16 + s] - t0) * 1e-3 : -1.0, (s == 1) ? " |" : "");
+        fprintf(stderr, "\n");
+      }
+    }
+    const double nw = std::max(1, P.grid - 2);
+    fprintf(stderr, "[chol dag] workers (mean cycles): wait %.0f trsm %.0f upd %.0f inv %.0f tasks %.1f total %.0f\n", w / nw, tr / nw, up / nw,
+            iv / nw, nt / nw, tot / nw);
+  }
   return STBA_OK;
 }
 
@@ -909,6 +2033,10 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
     CKC(cudaMemset(P->Linv, 0, (size_t)T * NB * NB * sizeof(double)));   // upper triangles stay zero forever
     CKC(cudaMalloc(&P->ybuf, (size_t)T * NB * sizeof(double)));
     CKC(cudaMalloc(&P->flags, (size_t)T * sizeof(int)));
+    CKC(cudaFuncSetAttribute(k_trsv_bwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM));
+    P->dag = getenv("STBA_CHOL_GRAPH") == nullptr;
+    if (P->dag) { if (build_dag_plan(*P) != STBA_OK) return STBA_ERR_CUDA; }
+    if (!P->dag) {
     {
       // tile lists: for step k, [panel rows | column k+1 strip | the rest], stored back to back
       std::vector<int2> h;
@@ -954,6 +2082,13 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
     ce = cudaGraphInstantiate(&P->exec, graph, 0);
     cudaGraphDestroy(graph);
     CKC(ce);
+    }
+  }
+  if (P->dag) {
+    const int r = run_dag(*P, stream);
+    if (r != STBA_OK) return r;
+    if (n_launches) *n_launches += P->launches;
+    return STBA_OK;
   }
   CKC(cudaGraphLaunch(P->exec, stream));
 #ifdef STBA_CHOL_TIMING
@@ -1016,8 +2151,10 @@ int chol_solve_with_factor(SolveWorkspace& ws, const double* S, int n, int ld, d
   }
   CKC(cudaMemsetAsync(P->flags, 0, 2 * (size_t)T * sizeof(int), stream));
   k_inv128<<<T, PT, POTRF_SMEM, stream>>>(S, ld, n, P->Linv);
-  k_trsv_fwd_all<<<T, TBA_THREADS, TBA_SMEM, stream>>>(S, ld, n, T, P->Linv, rhs, P->ybuf, P->flags, dev_info);
-  k_trsv_bwd_all<<<T, TBA_THREADS, TBA_SMEM, stream>>>(S, ld, n, T, P->Linv, P->ybuf, rhs, P->flags + T, dev_info);
+  for (int b0 = 0; b0 < T; b0 += substitution_chunk())
+    k_trsv_fwd_all<<<std::min(T - b0, substitution_chunk()), TBA_THREADS, TBA_SMEM, stream>>>(S, ld, n, T, P->Linv, rhs, P->ybuf, P->flags, dev_info, b0);
+  for (int b0 = 0; b0 < T; b0 += substitution_chunk())
+    k_trsv_bwd_all<<<std::min(T - b0, substitution_chunk()), TBA_THREADS, TBA_SMEM, stream>>>(S, ld, n, T, P->Linv, P->ybuf, rhs, P->flags + T, dev_info, b0);
   CKC(cudaGetLastError());
   if (n_launches) *n_launches += 3;
   return STBA_OK;
