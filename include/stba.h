@@ -220,6 +220,12 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
 #define STBA_UNIQUE_ID_BYTES 128
 int stba_comm_unique_id(char* id_out /* STBA_UNIQUE_ID_BYTES */);
 int stba_ba_comm_init(stba_ba* ba, int rank, int nranks, const char* id);
+/* A communicator that outlives one problem (ncclCommInitRank costs ~0.1-0.5 s): create it once per process,
+ * attach it to every problem with stba_ba_use_comm (the problem does not own it).  nranks <= 8. */
+typedef struct stba_comm stba_comm;
+int stba_comm_create(stba_comm** out, int device, int rank, int nranks, const char* unique_id);
+void stba_comm_destroy(stba_comm* c);
+int stba_ba_use_comm(stba_ba* ba, stba_comm* c);
 
 /* ==================================================================================== */
 /* Front of the path: the two stages that feed the BA problem.    */
@@ -270,6 +276,13 @@ int stba_calib_optimize(int device, int32_t n_views, const int32_t* view_ptr, co
                         const double* img_uv, double* intrinsics, double* distortion, double* poses,
                         int32_t max_iterations, double tolerance, int32_t* iterations_run,
                         double* update_norms, double* costs, int64_t* gpu_launches);
+/* same, plus device times (CUDA events on the solver's stream, nullable): the whole Gauss-Newton loop with the
+ * inputs already in HBM, and the sum over the iterations of the accumulation kernel alone (bench.py --workload CALIB) */
+int stba_calib_optimize_timed(int device, int32_t n_views, const int32_t* view_ptr, const double* obj_xy,
+                              const double* img_uv, double* intrinsics, double* distortion, double* poses,
+                              int32_t max_iterations, double tolerance, int32_t* iterations_run,
+                              double* update_norms, double* costs, int64_t* gpu_launches, float* loop_ms,
+                              float* accumulate_ms);
 
 /* ==================================================================================== */
 /* SE(3) pose graph (BASELINE.json configs[4]).  The reference has no      */
@@ -287,6 +300,12 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
                    const double* zt);
 void stba_pg_destroy(stba_pg* pg);
 int stba_pg_get_state(stba_pg* pg, double* q, double* t);
+int stba_pg_set_state(stba_pg* pg, const double* q, const double* t);
+/* device-side snapshot / restore of the poses, and the device time of the linearisation kernel alone
+ * (bench.py --workload PG) */
+int stba_pg_save_state(stba_pg* pg);
+int stba_pg_restore_state(stba_pg* pg);
+int stba_pg_time_linearize(stba_pg* pg, int reps, float* ms);
 /* one linearisation at the current state: cost = 1/2 |r|^2, gradient g f64[n,6], diagonal 6x6
  * blocks of J^T J Hdiag f64[n,36] (row-major), half-bandwidth in blocks.  Any output may be NULL. */
 int stba_pg_linearize(stba_pg* pg, double* cost, double* g, double* Hdiag, int32_t* bandwidth);

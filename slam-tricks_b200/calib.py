@@ -75,11 +75,14 @@ class CalibSolver:
 
     def totalOptimization(self, max_iterations=10, tolerance=1e-8):
         it = C.c_int32(0); nl = C.c_int64(0)
+        loop_ms = C.c_float(0); acc_ms = C.c_float(0)
         norms = np.zeros(max(max_iterations, 1)); costs = np.zeros(max(max_iterations, 1))
-        capi.check(capi.lib().stba_calib_optimize(self.device, self.cbsCount, capi.iptr(self.view_ptr), capi.dptr(self.obj), capi.dptr(self.img),
-                                                 capi.dptr(self.intrinsics), capi.dptr(self.distortion), capi.dptr(self.imgPos),
-                                                 max_iterations, tolerance, C.byref(it), capi.dptr(norms), capi.dptr(costs), C.byref(nl)),
-                   "stba_calib_optimize")
+        capi.check(capi.lib().stba_calib_optimize_timed(self.device, self.cbsCount, capi.iptr(self.view_ptr), capi.dptr(self.obj), capi.dptr(self.img),
+                                                       capi.dptr(self.intrinsics), capi.dptr(self.distortion), capi.dptr(self.imgPos),
+                                                       max_iterations, tolerance, C.byref(it), capi.dptr(norms), capi.dptr(costs), C.byref(nl),
+                                                       C.byref(loop_ms), C.byref(acc_ms)),
+                   "stba_calib_optimize_timed")
+        self.loop_ms, self.accumulate_ms = float(loop_ms.value), float(acc_ms.value)
         self.update_norms, self.costs, self.gpu_launches = norms[:it.value].tolist(), costs[:it.value].tolist(), int(nl.value)
         return self
 

@@ -113,15 +113,23 @@ SIGNATURES = {
     "stba_dense_cholesky_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _ip, C.c_int, C.POINTER(C.c_float)]),
     "stba_comm_unique_id": (C.c_int, [C.c_char_p]),
     "stba_ba_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "stba_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_char_p]),
+    "stba_comm_destroy": (None, [C.c_void_p]),
+    "stba_ba_use_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "stba_visibility": (C.c_int, [C.c_int, C.c_int32, C.c_int32, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int32, C.c_int64, _lp,
                                   _ip, _ip, _ip, _ip, _dp, _ip]),
     "stba_triangulate": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp, _ip, _ip, _dp, C.POINTER(Options),
                                    _ip, _dp, _ip, C.POINTER(C.c_float)]),
     "stba_calib_initialize": (C.c_int, [C.c_int32, _ip, _dp, _dp, _dp, _dp, _dp]),
     "stba_calib_optimize": (C.c_int, [C.c_int, C.c_int32, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int32, C.c_double, _ip, _dp, _dp, _lp]),
+    "stba_calib_optimize_timed": (C.c_int, [C.c_int, C.c_int32, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int32, C.c_double, _ip, _dp, _dp, _lp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "stba_pg_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int64, _dp, _dp, _ip, _ip, _dp, _dp]),
     "stba_pg_destroy": (None, [C.c_void_p]),
     "stba_pg_get_state": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "stba_pg_set_state": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "stba_pg_save_state": (C.c_int, [C.c_void_p]),
+    "stba_pg_restore_state": (C.c_int, [C.c_void_p]),
+    "stba_pg_time_linearize": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "stba_pg_linearize": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _ip]),
     "stba_pg_solve": (C.c_int, [C.c_void_p, C.POINTER(Options), C.POINTER(SummaryStruct), ITERATION_CALLBACK, C.c_void_p]),
     "stba_problem_create": (C.c_int, [C.POINTER(C.c_void_p)]),

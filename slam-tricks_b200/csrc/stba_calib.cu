@@ -488,6 +488,14 @@ int stba_calib_initialize(int32_t n_views, const int32_t* view_ptr, const double
 int stba_calib_optimize(int device, int32_t n_views, const int32_t* view_ptr, const double* obj_xy, const double* img_uv,
                         double* intrinsics, double* distortion, double* poses, int32_t max_iterations, double tolerance,
                         int32_t* iterations_run, double* update_norms, double* costs, int64_t* gpu_launches) {
+  return stba_calib_optimize_timed(device, n_views, view_ptr, obj_xy, img_uv, intrinsics, distortion, poses, max_iterations, tolerance,
+                                   iterations_run, update_norms, costs, gpu_launches, nullptr, nullptr);
+}
+
+int stba_calib_optimize_timed(int device, int32_t n_views, const int32_t* view_ptr, const double* obj_xy, const double* img_uv,
+                              double* intrinsics, double* distortion, double* poses, int32_t max_iterations, double tolerance,
+                              int32_t* iterations_run, double* update_norms, double* costs, int64_t* gpu_launches,
+                              float* loop_ms, float* accumulate_ms) {
   if (bad_views(n_views, view_ptr) || n_views > 1024 || !obj_xy || !img_uv || !intrinsics || !distortion || !poses || max_iterations < 0)
     return STBA_ERR_INVALID_ARGUMENT;
   int ndev = 0;
@@ -527,19 +535,40 @@ int stba_calib_optimize(int device, int32_t n_views, const int32_t* view_ptr, co
   int64_t launches = 0;
   int status = STBA_OK;
   const int solve_threads = std::max(64, ((n_views + 31) / 32) * 32);
+  // optional device timing (bench.py --workload CALIB): the whole Gauss-Newton loop with the inputs resident,
+  // and the accumulation kernel alone
+  const bool timed = loop_ms || accumulate_ms;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+  float acc_total = 0.f;
+  if (timed) {
+    cudaEventCreate(&ev_a); cudaEventCreate(&ev_b); cudaEventCreate(&ev_k0); cudaEventCreate(&ev_k1);
+    cudaEventRecord(ev_a, s);
+  }
   for (; it < max_iterations;) {                            // calib.cpp:298
+    if (timed) cudaEventRecord(ev_k0, s);
     k_calib_accumulate<<<n_views, kAccThreads, 0, s>>>(d_ptr, d_obj, d_img, d_param, d_pose, d_blocks);
+    if (timed) cudaEventRecord(ev_k1, s);
     k_calib_solve<<<1, solve_threads, 0, s>>>(n_views, d_blocks, d_param, d_pose, d_work, d_scal);
     launches += 2;
     double sc[3];
     CKC(cudaMemcpyAsync(sc, d_scal, sizeof(sc), cudaMemcpyDeviceToHost, s));
     CKC(cudaStreamSynchronize(s));
     CKC(cudaGetLastError());
+    if (timed) { float ms = 0.f; cudaEventElapsedTime(&ms, ev_k0, ev_k1); acc_total += ms; }
     if (update_norms) update_norms[it] = sc[0];
     if (costs) costs[it] = sc[1];
     ++it;
     if (sc[2] != 0.0 || !std::isfinite(sc[0])) { status = STBA_ERR_SOLVER; break; }
     if (sc[0] < tolerance) break;                           // calib.cpp:404
+  }
+  if (timed) {
+    cudaEventRecord(ev_b, s);
+    cudaEventSynchronize(ev_b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev_a, ev_b);
+    if (loop_ms) *loop_ms = ms;
+    if (accumulate_ms) *accumulate_ms = acc_total;
+    cudaEventDestroy(ev_a); cudaEventDestroy(ev_b); cudaEventDestroy(ev_k0); cudaEventDestroy(ev_k1);
   }
   CKC(cudaMemcpyAsync(h_param.data(), d_param, 9 * sizeof(double), cudaMemcpyDeviceToHost, s));
   CKC(cudaMemcpyAsync(h_pose.data(), d_pose, h_pose.size() * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -130,7 +130,19 @@ struct Engine {
   size_t flush_n = 0;
   cudaEvent_t ev[PH_COUNT + 1] = {};
   ncclComm_t comm = nullptr;
+  bool comm_owned = true;      // false: attached with stba_ba_use_comm, lives in a stba_comm handle
   int rank = 0, nranks = 1;
+  // multi-GPU: send/receive buffer of the ONE collective per linearisation:
+  // [S, row-major packed lower | reduced rhs | H_cc | g_c | cost, |x_l|^2, |g_l|^2, max|g_l| per rank].  The local
+  // partial sums stay in Hcc / gc / scal, so reducing twice (a rejected step rebuilds S at a new radius from
+  // the cached linearisation) gives the same result.
+  double* red = nullptr;
+  size_t red_count = 0, off_rhs = 0, off_hcc = 0, off_gc = 0, off_tail = 0;
+  double radius_built = 0.0;
+  bool want_xnorm = false;
+  const double* Hcc_use() const { return nranks > 1 ? red + off_hcc : Hcc; }
+  const double* gc_use() const { return nranks > 1 ? red + off_gc : gc; }
+  int reduce_linearization(double radius, const stba_options& opt);
   std::vector<void*> allocs;
 
   // Stream-ordered allocation from the device's default memory pool, whose release threshold is
@@ -173,7 +185,7 @@ struct Engine {
     if (scal_host) { std::lock_guard<std::mutex> lk(g_pinned_mu); g_pinned_free.push_back(scal_host); }
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
-    if (comm) ncclCommDestroy(comm);
+    if (comm && comm_owned) ncclCommDestroy(comm);
     if (stream) cudaStreamDestroy(stream);
   }
 
@@ -497,14 +509,7 @@ int Engine::linearize() {
 
 // multi-GPU reduction of the camera blocks, Jacobi scales on first use, gradient norms
 int Engine::post_linearize(const stba_options& opt, bool want_grad) {
-  if (nranks > 1) {
-    // Hcc and gc are contiguous? no — two collectives in one group
-    CKN(ncclGroupStart());
-    CKN(ncclAllReduce(Hcc, Hcc, 21 * (size_t)n_cam, ncclDouble, ncclSum, comm, stream));
-    CKN(ncclAllReduce(gc, gc, 6 * (size_t)n_cam, ncclDouble, ncclSum, comm, stream));
-    CKN(ncclAllReduce(scal + SC_COST, scal + SC_COST, 1, ncclDouble, ncclSum, comm, stream));
-    CKN(ncclGroupEnd());
-  }
+  if (nranks > 1) return STBA_OK;     // everything that needs reduced camera blocks happens after the one collective (build_reduced)
   if (!have_scale) {
     const int m = std::max(n_cam, n_lm);
     if (m) LAUNCH(this, k_jacobi_scale, (m + 127) / 128, 128, n_cam, n_lm, opt.jacobi_scaling, Hcc, Hll, sc, sl);
@@ -513,13 +518,8 @@ int Engine::post_linearize(const stba_options& opt, bool want_grad) {
   if (want_grad) {
     const uint8_t* lc = has_lm_const ? lm_const : nullptr;
     // cameras are replicated: only rank 0 counts them before the sum
-    LAUNCH(this, k_grad_norm, grid_for(n_cam + n_lm, kBlock), kBlock, rank == 0 ? n_cam : 0, n_lm, cam_const, lc,
+    LAUNCH(this, k_grad_norm, grid_for(n_cam + n_lm, kBlock), kBlock, n_cam, n_lm, cam_const, lc,
            cam_q, gc, gl, partial, counter, scal + SC_G2);
-    if (nranks > 1) {
-      // k_grad_norm with n_cam = 0 indexes landmarks from 0: handled by passing n_cam = 0 above
-      CKR(allreduce_sum(scal + SC_G2, 1));
-      CKR(allreduce_max(scal + SC_GMAX, 1));
-    }
   }
   CK(cudaGetLastError());
   return STBA_OK;
@@ -529,6 +529,7 @@ int Engine::post_linearize(const stba_options& opt, bool want_grad) {
 int Engine::build_reduced(double radius, const stba_options& opt) {
   if (!linearized) return STBA_ERR_INVALID_ARGUMENT;
   if (linearize_only) return STBA_ERR_UNSUPPORTED;
+  if (nranks > 1) return reduce_linearization(radius, opt);
   const double inv_r = 1.0 / radius;
   const uint8_t* lc = has_lm_const ? lm_const : nullptr;
   if (n_cam) LAUNCH(this, k_cam_diag, (6 * n_cam + 127) / 128, 128, n_cam, Hcc, sc, opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dc2);
@@ -538,19 +539,65 @@ int Engine::build_reduced(double radius, const stba_options& opt) {
   if (n_free) {
     if (n_chunk)
       LAUNCH(this, k_schur_diag, n_chunk, 32, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
-    LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, S, ld, rhs,
-           nranks > 1 ? 0 : 1);
-    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, S, ld);
-    if (nranks > 1) {
-      CKN(ncclGroupStart());
-      CKN(ncclAllReduce(S, S, (size_t)ld * n, ncclDouble, ncclSum, comm, stream));
-      CKN(ncclAllReduce(rhs, rhs, (size_t)n, ncclDouble, ncclSum, comm, stream));
-      CKN(ncclGroupEnd());
-      LAUNCH(this, k_add_cam_blocks, (n_cam + 127) / 128, 128, n_cam, free_of, Hcc, gc, Dc2, S, ld, rhs);
-    }
+    LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, S, ld, rhs, 1, 0);
+    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, S, ld, 0);
   }
   CK(cudaGetLastError());
   reduced_built = true;
+  radius_built = radius;
+  return STBA_OK;
+}
+
+// Multi-GPU (landmark-sharded): this rank's partial Schur sums, straight into the packed send buffer, then ONE
+// all-reduce of [S | rhs | H_cc | g_c | scalars] and the camera-side work on the reduced values, identical on
+// every rank: Jacobi scale (first call), LM diagonal, S_ii += H_cc + D_c^2, rhs += g_c, gradient norms.
+int Engine::reduce_linearization(double radius, const stba_options& opt) {
+  if (!red) return STBA_ERR_INVALID_ARGUMENT;
+  const double inv_r = 1.0 / radius;
+  const uint8_t* lc = has_lm_const ? lm_const : nullptr;
+  const int m = std::max(n_cam, n_lm);
+  const bool first = !have_scale;
+  if (first && n_lm) LAUNCH(this, k_jacobi_scale, (n_lm + 127) / 128, 128, 0, n_lm, opt.jacobi_scaling, nullptr, Hll, sc, sl);
+  LAUNCH(this, k_schur_lm, grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, obs_uv, Rt, lm4, cam_const, lc, Hll, gl, sl,
+         opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dl2, Linv, hl, E);
+  if (n_obs) LAUNCH(this, k_schur_E, grid_for(n_obs, kBlock), kBlock, n_obs, obs_cam, obs_lm, obs_uv, Rt, lm4, cam_const, lc, Linv, E);
+  double* tail = red + off_tail;
+  if (n_free) {
+    if (n_chunk) LAUNCH(this, k_schur_diag, n_chunk, 32, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
+    LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, red, ld,
+           red + off_rhs, 0, 1);
+    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, red, ld, 1);
+  }
+  if (n_cam) {
+    CK(cudaMemcpyAsync(red + off_hcc, Hcc, 21 * (size_t)n_cam * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    CK(cudaMemcpyAsync(red + off_gc, gc, 6 * (size_t)n_cam * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  }
+  // landmark-side scalars of this rank
+  LAUNCH(this, k_grad_norm, grid_for(n_lm, kBlock), kBlock, 0, n_lm, cam_const, lc, cam_q, gc, gl, partial, counter, scal + SC_G2);
+  if (want_xnorm)
+    LAUNCH(this, k_x_norm, grid_for(n_lm, kBlock), kBlock, 0, n_lm, cam_const, lc, cam_q, cam_t, lm4, partial, counter, scal + SC_XNORM2);
+  LAUNCH(this, k_fill_tail, 1, 32, tail, rank, scal, (int)SC_COST, (int)SC_G2, (int)SC_GMAX, (int)SC_XNORM2);
+  CKN(ncclAllReduce(red, red, red_count, ncclDouble, ncclSum, comm, stream));
+  // ---- on the reduced values (replicated work, bit-identical on every rank) ----
+  if (first && n_cam) LAUNCH(this, k_jacobi_scale, (n_cam + 127) / 128, 128, n_cam, 0, opt.jacobi_scaling, Hcc_use(), nullptr, sc, sl);
+  have_scale = true;
+  (void)m;
+  if (n_cam) LAUNCH(this, k_cam_diag, (6 * n_cam + 127) / 128, 128, n_cam, Hcc_use(), sc, opt.min_lm_diagonal, opt.max_lm_diagonal, inv_r, Dc2);
+  if (n_free) {
+    const int tiles = (n + 31) / 32;
+    k_unpack_lower<<<dim3(tiles, tiles), 256, 0, stream>>>(red, n, S, ld);
+    ++launches;
+    CK(cudaMemcpyAsync(rhs, red + off_rhs, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    LAUNCH(this, k_add_cam_blocks, (n_cam + 127) / 128, 128, n_cam, free_of, Hcc_use(), gc_use(), Dc2, S, ld, rhs);
+  }
+  LAUNCH(this, k_grad_norm, grid_for(n_cam, kBlock), kBlock, n_cam, 0, cam_const, lc, cam_q, gc_use(), gl, partial, counter, scal + SC_G2);
+  if (want_xnorm)
+    LAUNCH(this, k_x_norm, grid_for(n_cam, kBlock), kBlock, n_cam, 0, cam_const, lc, cam_q, cam_t, lm4, partial, counter, scal + SC_XNORM2);
+  LAUNCH(this, k_combine_reduced, 1, 32, tail, nranks, want_xnorm ? 1 : 0, scal, (int)SC_COST, (int)SC_G2, (int)SC_GMAX, (int)SC_XNORM2);
+  want_xnorm = false;
+  CK(cudaGetLastError());
+  reduced_built = true;
+  radius_built = radius;
   return STBA_OK;
 }
 
@@ -594,7 +641,7 @@ int Engine::dense_solve(int backend) {
 int Engine::step_from_solution() {
   LAUNCH(this, k_backsub, grid_for(n_lm, kBlock), kBlock, n_lm, lm_ptr, obs_cam, E, yc, Linv, hl, gl, Dl2, lm4, yl, lm4_2,
          partial, counter, scal + SC_MCC_L);
-  LAUNCH(this, k_cam_update, grid_for(n_cam, kBlock), kBlock, n_cam, cam_const, cam_q, cam_t, yc, gc, Dc2, cam_q2, cam_t2,
+  LAUNCH(this, k_cam_update, grid_for(n_cam, kBlock), kBlock, n_cam, cam_const, cam_q, cam_t, yc, gc_use(), Dc2, cam_q2, cam_t2,
          partial, counter, scal + SC_MCC_C);
   CK(cudaGetLastError());
   return STBA_OK;
@@ -640,21 +687,24 @@ int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_cal
   };
 
   // ---- IterationZero ----
+  double radius = opt.initial_trust_region_radius;
   CK(cudaEventRecord(ev[0], stream));
   CKR(linearize());
-  CKR(post_linearize(opt, true));
-  {
+  if (nranks > 1) {
+    // the first reduced system is built here: its collective also carries H_cc, g_c, the cost and the norms
+    want_xnorm = true;
+    CKR(build_reduced(radius, opt));
+  } else {
+    CKR(post_linearize(opt, true));
     const uint8_t* lc = has_lm_const ? lm_const : nullptr;
-    LAUNCH(this, k_x_norm, grid_for(n_cam + n_lm, kBlock), kBlock, rank == 0 ? n_cam : 0, n_lm, cam_const, lc, cam_q, cam_t, lm4,
+    LAUNCH(this, k_x_norm, grid_for(n_cam + n_lm, kBlock), kBlock, n_cam, n_lm, cam_const, lc, cam_q, cam_t, lm4,
            partial, counter, scal + SC_XNORM2);
-    CKR(allreduce_sum(scal + SC_XNORM2, 1));
   }
   CK(cudaEventRecord(ev[1], stream));
   CKR(fetch_scalars());
   add_phase(PH_LIN, ev[0], ev[1]);
   double x_cost = scal_host[SC_COST];
   double x_norm = std::sqrt(scal_host[SC_XNORM2]);
-  double radius = opt.initial_trust_region_radius;
   double decrease_factor = 2.0;
   int num_invalid = 0;
   auto t_iter = clk::now();
@@ -699,7 +749,8 @@ int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_cal
 
     // ---- ComputeTrustRegionStep ----
     CK(cudaEventRecord(ev[0], stream));
-    CKR(build_reduced(radius, opt));
+    // multi-GPU: after an accepted step the system at this radius came with the linearisation's collective
+    if (!(nranks > 1 && reduced_built && radius_built == radius)) CKR(build_reduced(radius, opt));
     CK(cudaEventRecord(ev[1], stream));
     CKR(dense_solve(opt.dense_backend));
     CK(cudaEventRecord(ev[2], stream));
@@ -749,17 +800,18 @@ int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_cal
       // ---- accept: x <- x+, re-linearise ----
       std::swap(cam_q, cam_q2); std::swap(cam_t, cam_t2); std::swap(lm4, lm4_2); std::swap(Rt, Rt2);
       x_norm = std::sqrt(scal_host[SC_XN2_C] + scal_host[SC_XN2_L]);
+      radius = std::min(opt.max_trust_region_radius, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+      decrease_factor = 2.0;
       CK(cudaEventRecord(ev[0], stream));
       CKR(linearize());
-      CKR(post_linearize(opt, true));
+      if (nranks > 1) CKR(build_reduced(radius, opt));      // ONE collective: S | rhs | H_cc | g_c | cost | gradient norms
+      else CKR(post_linearize(opt, true));
       CK(cudaEventRecord(ev[1], stream));
       CKR(fetch_scalars());
       add_phase(PH_LIN, ev[0], ev[1]);
       x_cost = scal_host[SC_COST];
       it.cost = x_cost; it.gradient_norm = std::sqrt(scal_host[SC_G2]); it.gradient_max_norm = scal_host[SC_GMAX];
       it.step_is_successful = 1;
-      radius = std::min(opt.max_trust_region_radius, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
-      decrease_factor = 2.0;
     } else {
       it.cost = cand_ok ? cand_cost : x_cost;
       radius /= decrease_factor;
@@ -938,6 +990,7 @@ int stba_ba_get_blocks(stba_ba* ba, double* Hcc, double* gc, double* Hll, double
   Engine& e = ba->e;
   CK(cudaSetDevice(e.device));
   CK(cudaStreamSynchronize(e.stream));
+  // (multi-GPU: this rank's partial sums — the reduced blocks only exist after stba_ba_reduced_system / solve)
   if (Hcc && e.n_cam) CK(cudaMemcpy(Hcc, e.Hcc, 21 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToHost));
   if (gc && e.n_cam) CK(cudaMemcpy(gc, e.gc, 6 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToHost));
   if (Hll && e.n_lm) CK(cudaMemcpy(Hll, e.Hll, 6 * (size_t)e.n_lm * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1172,15 +1225,75 @@ int stba_comm_unique_id(char* id_out) {
   return STBA_OK;
 }
 
+struct stba_comm {
+  ncclComm_t comm = nullptr;
+  int device = 0, rank = 0, nranks = 1;
+};
+
+int stba_comm_create(stba_comm** out, int device, int rank, int nranks, const char* id) {
+  if (!out || !id || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return STBA_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STBA_ERR_NO_DEVICE; }
+  if (device < 0 || device >= ndev) return STBA_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(device));
+  stba_comm* c = new (std::nothrow) stba_comm();
+  if (!c) return STBA_ERR_CUDA;
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  const ncclResult_t r = ncclCommInitRank(&c->comm, nranks, uid, rank);
+  if (r != ncclSuccess) { delete c; return STBA_ERR_COMM; }
+  c->device = device; c->rank = rank; c->nranks = nranks;
+  *out = c;
+  return STBA_OK;
+}
+
+void stba_comm_destroy(stba_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm) ncclCommDestroy(c->comm);
+  delete c;
+}
+
+static int attach_comm(Engine& e, ncclComm_t comm, bool owned, int rank, int nranks);
+
+int stba_ba_use_comm(stba_ba* ba, stba_comm* c) {
+  if (!ba || !c || c->device != ba->e.device) return STBA_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ba->e.device));
+  return attach_comm(ba->e, c->comm, false, c->rank, c->nranks);
+}
+
 int stba_ba_comm_init(stba_ba* ba, int rank, int nranks, const char* id) {
   if (!ba || !id || nranks < 1 || rank < 0 || rank >= nranks) return STBA_ERR_INVALID_ARGUMENT;
   Engine& e = ba->e;
   CK(cudaSetDevice(e.device));
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof(uid));
-  CKN(ncclCommInitRank(&e.comm, nranks, uid, rank));
+  if (nranks > 8) return STBA_ERR_UNSUPPORTED;     // the per-rank maxima travel in 8 slots of the collective
+  ncclComm_t comm = nullptr;
+  CKN(ncclCommInitRank(&comm, nranks, uid, rank));
+  return attach_comm(e, comm, true, rank, nranks);
+}
+
+static int attach_comm(Engine& e, ncclComm_t comm, bool owned, int rank, int nranks) {
+  if (e.comm && e.comm_owned) ncclCommDestroy(e.comm);
+  e.comm = comm;
+  e.comm_owned = owned;
   e.rank = rank;
   e.nranks = nranks;
+  if (nranks > 1 && !e.linearize_only && !e.red) {
+    const size_t n = (size_t)e.n;
+    e.off_rhs = (n * (n + 1) / 2 + 1) & ~(size_t)1;
+    e.off_hcc = (e.off_rhs + n + 1) & ~(size_t)1;
+    e.off_gc = e.off_hcc + 21 * (size_t)e.n_cam;
+    e.off_tail = (e.off_gc + 6 * (size_t)e.n_cam + 1) & ~(size_t)1;
+    e.red_count = e.off_tail + 16;
+    CKR(e.alloc(&e.red, e.red_count));
+    CK(cudaMemsetAsync(e.red, 0, e.red_count * sizeof(double), e.stream));
+    CK(cudaStreamSynchronize(e.stream));
+  }
+  e.linearized = false;
+  e.reduced_built = false;
   return STBA_OK;
 }
 

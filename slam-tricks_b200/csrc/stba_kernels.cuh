@@ -220,7 +220,7 @@ __global__ void k_schur_diag_finish(int n_cam, const int* __restrict__ cam_chunk
                                     const int* __restrict__ free_of, const double* __restrict__ chunk_acc,
                                     const double* __restrict__ Hcc, const double* __restrict__ gc,
                                     const double* __restrict__ Dc2, double* __restrict__ S, int n,
-                                    double* __restrict__ rhs, int include_cam) {
+                                    double* __restrict__ rhs, int include_cam, int packed) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_cam) return;
   const int f = free_of[c];
@@ -241,8 +241,13 @@ __global__ void k_schur_diag_finish(int n_cam, const int* __restrict__ cam_chunk
         v += Hcc[(size_t)c * 21 + t];
         if (i == j) v += Dc2[(size_t)c * 6 + i];
       }
-      S[(size_t)(6 * f + i) + (size_t)(6 * f + j) * n] = v;
-      S[(size_t)(6 * f + j) + (size_t)(6 * f + i) * n] = v;
+      if (packed) {          // multi-GPU send buffer: row-major packed lower triangle, (r, c <= r) at r (r + 1) / 2 + c
+        const size_t r = 6 * f + j, cc = 6 * f + i;
+        S[r * (r + 1) / 2 + cc] = v;
+      } else {
+        S[(size_t)(6 * f + i) + (size_t)(6 * f + j) * n] = v;
+        S[(size_t)(6 * f + j) + (size_t)(6 * f + i) * n] = v;
+      }
     }
 #pragma unroll
   for (int i = 0; i < 6; ++i) rhs[6 * f + i] = (include_cam ? gc[(size_t)c * 6 + i] : 0.0) - a[21 + i];
@@ -277,7 +282,7 @@ __global__ void k_add_cam_blocks(int n_cam, const int* __restrict__ free_of, con
 // no atomics, no zero-fill, every block written exactly once.
 __global__ void __launch_bounds__(kBlock)
 k_schur_off(int64_t n_blk, const int64_t* __restrict__ blk_ptr, const uint64_t* __restrict__ inc,
-            const double* __restrict__ E, double* __restrict__ S, int n) {
+            const double* __restrict__ E, double* __restrict__ S, int n, int packed) {
   for (int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x; b < n_blk; b += (int64_t)gridDim.x * kBlock) {
     // b = i (i-1) / 2 + j,  i > j >= 0
     int64_t i = (int64_t)((1.0 + sqrt(1.0 + 8.0 * (double)b)) * 0.5);
@@ -303,6 +308,16 @@ k_schur_off(int64_t n_blk, const int64_t* __restrict__ blk_ptr, const uint64_t* 
         for (int c = 0; c < 6; ++c)
           acc[6 * c + r] = fma(ea[3 * r], eb[3 * c], fma(ea[3 * r + 1], eb[3 * c + 1], fma(ea[3 * r + 2], eb[3 * c + 2], acc[6 * c + r])));
     }
+    if (packed) {            // row-major packed lower triangle (multi-GPU send buffer)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const size_t row = 6 * i + r;
+        double* dst = S + row * (row + 1) / 2 + 6 * j;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dst[c] = -acc[6 * c + r];
+      }
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
       double2* col = reinterpret_cast<double2*>(S + (size_t)(6 * i) + (size_t)(6 * j + c) * n);
@@ -311,6 +326,48 @@ k_schur_off(int64_t n_blk, const int64_t* __restrict__ blk_ptr, const uint64_t* 
       col[2] = make_double2(-acc[6 * c + 4], -acc[6 * c + 5]);
     }
   }
+}
+
+// multi-GPU: the reduced packed lower triangle (row-major: (r, c <= r) at r (r + 1) / 2 + c) back into the
+// column-major S the factorisation works on, through a 32 x 32 shared-memory transpose (both sides coalesced).
+// grid: (tiles, tiles), tile (x = column tile, y = row tile), only y >= x does work.
+__global__ void __launch_bounds__(256) k_unpack_lower(const double* __restrict__ Sp, int n, double* __restrict__ S, int ld) {
+  __shared__ double tile[32][33];
+  const int tc = blockIdx.x, tr = blockIdx.y;
+  if (tr < tc) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = tr * 32 + ty + 8 * k, c = tc * 32 + tx;
+    tile[ty + 8 * k][tx] = (r < n && c <= r) ? Sp[(size_t)r * (r + 1) / 2 + c] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = tc * 32 + ty + 8 * k, r = tr * 32 + tx;
+    if (r < n && c <= r) S[(size_t)c * ld + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+// multi-GPU: scalars of the one collective.  tail = [cost, |x_l|^2, |g_l|^2, max|g_l| per rank (8 slots)] after the
+// sum-reduce; cam = camera-side [sum of squares, max] of the gradient (identical on every rank).
+__global__ void k_combine_reduced(const double* __restrict__ tail, int nranks, int with_xnorm, double* __restrict__ scal, int sc_cost,
+                                  int sc_g2, int sc_gmax, int sc_xnorm2) {
+  if (threadIdx.x || blockIdx.x) return;
+  scal[sc_cost] = tail[0];
+  if (with_xnorm) scal[sc_xnorm2] += tail[1];
+  scal[sc_g2] += tail[2];
+  double m = scal[sc_gmax];
+  for (int r = 0; r < nranks && r < 8; ++r) m = fmax(m, tail[3 + r]);
+  scal[sc_gmax] = m;
+}
+__global__ void k_fill_tail(double* __restrict__ tail, int rank, const double* __restrict__ scal, int sc_cost, int sc_g2, int sc_gmax,
+                            int sc_xnorm2) {
+  if (threadIdx.x || blockIdx.x) return;
+  tail[0] = scal[sc_cost];
+  tail[1] = scal[sc_xnorm2];
+  tail[2] = scal[sc_g2];
+  for (int r = 0; r < 8; ++r) tail[3 + r] = (r == rank) ? scal[sc_gmax] : 0.0;
 }
 
 // scatter the reduced solution into per-camera rows (zero for constant cameras)

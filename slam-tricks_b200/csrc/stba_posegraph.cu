@@ -842,6 +842,7 @@ struct stba_pg {
   int *ei = nullptr, *ej = nullptr, *inc_ptr = nullptr, *inc_edge = nullptr, *info = nullptr;
   double *band = nullptr, *A = nullptr, *g = nullptr, *gs = nullptr, *ys = nullptr, *scale = nullptr, *diag = nullptr;
   double *share = nullptr, *red = nullptr, *red_host = nullptr;
+  double *save_q = nullptr, *save_t = nullptr;
   bool have_scale = false;
   // partitioned band solve (P > 1): interiors [pi0, pi1), separators of B columns in between
   int P = 1, Br = 1;
@@ -1014,6 +1015,51 @@ int stba_pg_get_state(stba_pg* pg, double* q, double* t) {
   return STBA_OK;
 }
 
+int stba_pg_set_state(stba_pg* pg, const double* q, const double* t) {
+  if (!pg || !q || !t) return STBA_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(pg->device));
+  CK(cudaMemcpyAsync(pg->q, q, 4 * (size_t)pg->n * sizeof(double), cudaMemcpyHostToDevice, pg->s));
+  CK(cudaMemcpyAsync(pg->t, t, 3 * (size_t)pg->n * sizeof(double), cudaMemcpyHostToDevice, pg->s));
+  CK(cudaStreamSynchronize(pg->s));
+  return STBA_OK;
+}
+
+// device-side snapshot of the poses (benchmarks restore x0 without touching the host)
+int stba_pg_save_state(stba_pg* pg) {
+  if (!pg) return STBA_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(pg->device));
+  if (!pg->save_q) { int r = pg->alloc(&pg->save_q, 4 * (size_t)pg->n); if (r != STBA_OK) return r; r = pg->alloc(&pg->save_t, 3 * (size_t)pg->n); if (r != STBA_OK) return r; }
+  CK(cudaMemcpyAsync(pg->save_q, pg->q, 4 * (size_t)pg->n * sizeof(double), cudaMemcpyDeviceToDevice, pg->s));
+  CK(cudaMemcpyAsync(pg->save_t, pg->t, 3 * (size_t)pg->n * sizeof(double), cudaMemcpyDeviceToDevice, pg->s));
+  CK(cudaStreamSynchronize(pg->s));
+  return STBA_OK;
+}
+int stba_pg_restore_state(stba_pg* pg) {
+  if (!pg || !pg->save_q) return STBA_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(pg->device));
+  CK(cudaMemcpyAsync(pg->q, pg->save_q, 4 * (size_t)pg->n * sizeof(double), cudaMemcpyDeviceToDevice, pg->s));
+  CK(cudaMemcpyAsync(pg->t, pg->save_t, 3 * (size_t)pg->n * sizeof(double), cudaMemcpyDeviceToDevice, pg->s));
+  return STBA_OK;
+}
+
+// device time of `reps` launches of the linearisation kernel alone (CUDA events on the solver's stream)
+int stba_pg_time_linearize(stba_pg* pg, int reps, float* ms) {
+  if (!pg || reps < 1 || !ms) return STBA_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(pg->device));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  for (int r = 0; r < reps; ++r) {
+    CK(cudaEventRecord(a, pg->s));
+    k_pg_linearize<<<(pg->n + 63) / 64, 64, 0, pg->s>>>(pg->n, pg->B, pg->q, pg->t, pg->inc_ptr, pg->inc_edge, pg->ei, pg->ej, pg->zq, pg->zt, pg->band,
+                                                     pg->g, pg->share);
+    CK(cudaEventRecord(b, pg->s));
+    CK(cudaStreamSynchronize(pg->s));
+    CK(cudaEventElapsedTime(&ms[r], a, b));
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return STBA_OK;
+}
+
 int stba_pg_linearize(stba_pg* pg, double* cost, double* g, double* Hdiag, int32_t* bandwidth) {
   if (!pg) return STBA_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(pg->device));
@@ -1034,6 +1080,7 @@ int stba_pg_solve(stba_pg* pg, const stba_options* opt, stba_summary* sum, stba_
   stba_options o;
   if (opt) o = *opt; else stba_options_init(&o);
   const int n = pg->n, B = pg->B;
+  pg->have_scale = false;      // Jacobi scaling is computed at the x0 of THIS solve (as Ceres does)
   const auto t_start = std::chrono::steady_clock::now();
   const int64_t launches0 = pg->launches;
   auto record = [&](const stba_iteration& it) -> int {

@@ -164,6 +164,9 @@ class BAEngine:
     def launch_count(self):
         return int(self._L.stba_ba_launch_count(self._h))
 
+    def use_comm(self, comm):
+        capi.check(self._L.stba_ba_use_comm(self._h, comm._h), "stba_ba_use_comm")
+
     def comm_init(self, rank, nranks, unique_id):
         capi.check(self._L.stba_ba_comm_init(self._h, rank, nranks, unique_id), "stba_ba_comm_init")
 
@@ -183,6 +186,20 @@ def peak_fp64(device=0, reps=5):
     v = C.c_double(0)
     capi.check(capi.lib().stba_peak_fp64(device, reps, C.byref(v)), "stba_peak_fp64")
     return v.value
+
+
+class Comm:
+    """A NCCL communicator that outlives one problem (`stba_comm_create`); attach with `BAEngine.use_comm`."""
+
+    def __init__(self, rank, nranks, unique_id, device=0):
+        self._h = C.c_void_p()
+        self._L = capi.lib()
+        capi.check(self._L.stba_comm_create(C.byref(self._h), device, rank, nranks, unique_id), "stba_comm_create")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.stba_comm_destroy(self._h)
+            self._h = None
 
 
 def comm_unique_id():

@@ -56,6 +56,20 @@ class PoseGraph:
     def solve(self, options=None, callback=None):
         return engine.run_solve(self._L.stba_pg_solve, self._h, options, callback)
 
+    def set_state(self, q, t):
+        capi.check(self._L.stba_pg_set_state(self._h, capi.dptr(capi.as_f64(q, (self.n, 4))), capi.dptr(capi.as_f64(t, (self.n, 3)))), "stba_pg_set_state")
+
+    def save_state(self):
+        capi.check(self._L.stba_pg_save_state(self._h), "stba_pg_save_state")
+
+    def restore_state(self):
+        capi.check(self._L.stba_pg_restore_state(self._h), "stba_pg_restore_state")
+
+    def time_linearize(self, reps=10):
+        ms = (C.c_float * reps)()
+        capi.check(self._L.stba_pg_time_linearize(self._h, reps, ms), "stba_pg_time_linearize")
+        return np.array(list(ms), dtype=np.float64)
+
     def get_state(self):
         q = np.zeros((self.n, 4)); t = np.zeros((self.n, 3))
         capi.check(self._L.stba_pg_get_state(self._h, capi.dptr(q), capi.dptr(t)), "stba_pg_get_state")

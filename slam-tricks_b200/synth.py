@@ -383,3 +383,33 @@ def pose_graph(n=200, offsets=(1, 2, 3, 4), sigma_t=0.01, sigma_r=0.005, drift_t
     for i in range(1, n):
         q0[i], t0[i] = _se3_compose(q0[i - 1], t0[i - 1], sq[i - 1], st[i - 1])
     return dict(q0=q0, t0=t0, ei=ei, ej=ej, zq=zq, zt=zt, q_truth=qT, t_truth=tT)
+
+
+def calib_views(n_views=20, rows=8, cols=11, cb_size=2.8e-2, seed=20221107, noise_px=0.1):
+    """Synthetic Zhang-calibration input of BASELINE.json configs[3] (20 views x 88 corners; the reference ships 9 x 40
+    only): a known pinhole camera with the reference's distortion model (st3-calibration/src/src/calib.cpp:254-262),
+    corner (i, j) at board coordinates (j, i) * cb_size (calib.cpp:11-36), pixels rounded to 3 decimals and through
+    float32 as `CBCorners::write` / `read` do (cbcorner.cpp:34-72).  Returns (objs, imgs, K4, D5)."""
+    rng = np.random.default_rng(seed)
+    K4 = np.array([3200.0, 3180.0, 2010.0, 1490.0])
+    D5 = np.array([0.08, -0.15, 0.05, 1e-3, -8e-4])
+    j, i = np.meshgrid(np.arange(cols), np.arange(rows))
+    obj = np.stack([j.ravel() * cb_size, i.ravel() * cb_size], axis=-1).astype(np.float64)
+    centre = np.array([0.5 * (cols - 1) * cb_size, 0.5 * (rows - 1) * cb_size, 0.0])
+    objs, imgs = [], []
+    for _ in range(n_views):
+        om = rng.normal(0, 0.25, 3)
+        th = np.linalg.norm(om)
+        Kx = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]])
+        R = np.eye(3) + (np.sin(th) / th) * Kx + ((1 - np.cos(th)) / th ** 2) * (Kx @ Kx) if th > 1e-12 else np.eye(3)
+        t = np.array([rng.normal(0, 0.03), rng.normal(0, 0.03), 0.55 + rng.uniform(-0.1, 0.15)]) - R @ centre
+        P = (R @ np.stack([obj[:, 0], obj[:, 1], np.zeros(len(obj))])).T + t
+        xn, yn = P[:, 0] / P[:, 2], P[:, 1] / P[:, 2]
+        r2 = xn * xn + yn * yn
+        rad = 1 + D5[0] * r2 + D5[1] * r2 ** 2 + D5[2] * r2 ** 3
+        xd = xn * rad + 2 * D5[3] * xn * yn + D5[4] * (r2 + 2 * xn * xn)
+        yd = yn * rad + 2 * D5[4] * xn * yn + D5[3] * (r2 + 2 * yn * yn)
+        uv = np.stack([K4[0] * xd + K4[2], K4[1] * yd + K4[3]], axis=-1) + rng.normal(0, noise_px, (len(obj), 2))
+        objs.append(obj.copy())
+        imgs.append(np.round(uv, 3).astype(np.float32).astype(np.float64))
+    return objs, imgs, K4, D5
