@@ -256,6 +256,7 @@ static int run_bound() {   // ceres_bound.cpp:27-65
     ceres::Solver::Summary summary;
     ceres::Solve(options, &problem, &summary);
     printf("unbounded: x = %.9f gpu=%d %s\n", x, (int)summary.ran_on_gpu, summary.BriefReport().c_str());
+    for (const auto& it : summary.iterations) printf("trace %d %.17g %.17g\n", it.iteration, it.cost, it.trust_region_radius);
   }
   double y = 0.5;
   {
@@ -285,6 +286,9 @@ static int run_curve() {
   ceres::Solve(options, &problem, &summary);
   printf("curve: a=%.6f b=%.6f c=%.6f residual blocks=%d gpu=%d %s\n", abc[0], abc[1], abc[2], problem.NumResidualBlocks(), (int)summary.ran_on_gpu,
          summary.BriefReport().c_str());
+  for (const auto& it : summary.iterations)      // compared with oracle/dense_lm.py iterate for iterate (tests/test_cpp_shim.py)
+    printf("trace %d %.17g %.17g %.17g %d\n", it.iteration, it.cost, it.trust_region_radius, it.step_norm, (int)it.step_is_successful);
+  printf("final %.17g %.17g %.17g\n", abc[0], abc[1], abc[2]);
   return (std::fabs(abc[0] - 1) < 0.02 && std::fabs(abc[1] - 2) < 0.02 && std::fabs(abc[2] - 3) < 0.1 && summary.termination_type == ceres::CONVERGENCE) ? 0 : 1;
 }
 

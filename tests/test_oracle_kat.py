@@ -176,3 +176,90 @@ def test_c_twin_equals_numpy_oracle(scene_small):
     for a, b in zip(s.iterations, s2.iterations):
         assert abs(a["cost"] - b["cost"]) <= 1e-10 * max(a["cost"], 1e-300)
         assert abs(a["relative_decrease"] - b["relative_decrease"]) < 1e-8
+
+
+# ---- pinned against outputs of the reference's OWN code (tests/golden/ref_kat.npz, made by make_ref_kat.py) -------
+import os as _os
+
+_REF_KAT = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "ref_kat.npz")
+
+
+@pytest.fixture(scope="module")
+def ref_kat():
+    z = np.load(_REF_KAT)
+    c, o = z["cases"], z["out"]
+    return dict(q=c[:, :4], t=c[:, 4:7], P=c[:, 7:10], uv=c[:, 10:12], delta=c[:, 12:15],
+                r=o[:, 0:2], Jq=o[:, 2:10].reshape(-1, 2, 4), Jt=o[:, 10:16].reshape(-1, 2, 3), JP=o[:, 16:22].reshape(-1, 2, 3),
+                plus=o[:, 22:26], lpJ=o[:, 26:38].reshape(-1, 4, 3), tri_r=o[:, 38:40], tri_J=o[:, 40:46].reshape(-1, 2, 3),
+                log=o[:, 46:49], pnp_r=o[:, 49:51], pnp_JR=o[:, 51:57].reshape(-1, 2, 3), pnp_Jt=o[:, 57:63].reshape(-1, 2, 3),
+                plus3=o[:, 63:66], gn_pose=z["gn_pose"], gn_iter_num=int(z["gn_iter_num"]))
+
+
+def test_residual_and_exact_jacobian_equal_jet_autodiff_of_the_reference_functor(ref_kat):
+    # ProjectFactor::operator()<Jet> (test_ceres.h:63-80) differentiated by ceres::Jet through the Sophus / Eigen calls
+    # of the reference text, chained with LieLocalParameterization::ComputeJacobian (:32-38) = what Ceres hands its
+    # linear solver; the oracle's closed form must be that Jacobian
+    k = ref_kat
+    n = len(k["q"])
+    idx = np.arange(n, dtype=np.int32)
+    r, Jc, Jl = bo.residual_jacobian(k["q"], k["t"], k["P"], idx, idx, k["uv"])
+    assert np.max(np.abs(r - k["r"])) < 1e-13
+    J_theta = np.einsum("nij,njk->nik", k["Jq"], k["lpJ"])
+    scale = np.maximum(1.0, np.abs(Jc).max(axis=(1, 2)))[:, None, None]
+    assert np.max(np.abs(Jc[:, :, :3] - J_theta) / scale) < 1e-12
+    assert np.max(np.abs(Jc[:, :, 3:] - k["Jt"]) / scale) < 1e-12
+    assert np.max(np.abs(Jl - k["JP"]) / scale) < 1e-12
+
+
+def test_manifold_equals_the_reference_parameterizations(ref_kat):
+    k = ref_kat
+    for q, d, want, J in zip(k["q"], k["delta"], k["plus"], k["lpJ"]):
+        assert np.max(np.abs(lie.so3_plus(q, d) - want)) < 1e-15       # LieLocalParameterization<SO3d>::Plus
+        assert np.max(np.abs(lie.so3_plus_jacobian(q) - J)) < 1e-15    # ::ComputeJacobian
+    # so3.log() and LieR3LocalParameterization::Plus (solver.hpp:67-78): x <- Log(Exp(x) Exp(delta)), up to the 2 pi branch
+    for q, d, w, wp in zip(k["q"], k["delta"], k["log"], k["plus3"]):
+        mine = lie.so3_log_quat(q)
+        assert min(np.abs(mine - w).max(), np.abs(lie.quat_mul(lie.so3_exp_quat(mine), lie.so3_exp_quat(-w)) - [0, 0, 0, 1]).max(),
+                   np.abs(lie.quat_mul(lie.so3_exp_quat(mine), lie.so3_exp_quat(-w)) + [0, 0, 0, 1]).max()) < 1e-12
+        got = lie.so3_exp_quat(lie.so3_log_quat(lie.quat_mul(lie.so3_exp_quat(w), lie.so3_exp_quat(d))))
+        ref = lie.so3_exp_quat(wp)
+        assert min(np.abs(got - ref).max(), np.abs(got + ref).max()) < 1e-12
+
+
+def test_triangulation_functor_equals_the_reference(ref_kat):
+    from oracle import front_oracle as fo
+    k = ref_kat
+    R, tcw = fo.world_to_camera(k["q"], k["t"])
+    for i in range(len(k["q"])):
+        r, J = fo.triangulation_residual_jacobian(R[i:i + 1], tcw[i:i + 1], k["uv"][i:i + 1], k["P"][i])
+        assert np.max(np.abs(r - k["tri_r"][i])) < 1e-13
+        assert np.max(np.abs(J - k["tri_J"][i])) < 1e-12 * max(1.0, np.abs(J).max())
+
+
+def test_reference_hand_jacobian_and_gauss_newton_reproduced(ref_kat, stba):
+    k = ref_kat
+    for i in range(len(k["q"])):        # PnPSizedCostFunction::Evaluate, solver.hpp:168-212
+        e_R, e_t = bo.pnp_reference_jacobian(k["q"][i], k["t"][i], k["P"][i])
+        s = max(1.0, np.abs(e_R).max())
+        assert np.max(np.abs(e_R - k["pnp_JR"][i])) < 1e-11 * s and np.max(np.abs(e_t - k["pnp_Jt"][i])) < 1e-12 * s
+        assert np.max(np.abs(k["pnp_r"][i] - k["r"][i])) < 1e-12
+    # SelfGaussNewton (solver.hpp:387-462) run from the reference source: same pose, same `iter num`
+    s = stba.synth.pnp_scene()
+    q, t = s["q_init"].copy(), s["t_init"].copy()
+    it = 0
+    for it in range(10):
+        H = np.zeros((6, 6)); g = np.zeros(6)
+        R = lie.quat_to_rot(q)
+        for P, uv in zip(s["points"], s["uv"]):
+            pc = R.T @ (P - t)
+            r = pc[:2] / pc[2] - uv
+            e_R, e_t = bo.pnp_reference_jacobian(q, t, P)
+            J = np.concatenate([e_R, e_t], axis=1)
+            H += J.T @ J; g -= J.T @ r
+        d = np.linalg.solve(H, g)
+        q = lie.so3_plus(q, d[:3]); t = t + d[3:]
+        if np.linalg.norm(d[:3]) + np.linalg.norm(d[3:]) < 1e-8:
+            break
+    assert it == k["gn_iter_num"]
+    assert min(np.abs(q - k["gn_pose"][:4]).max(), np.abs(q + k["gn_pose"][:4]).max()) < 1e-12
+    assert np.abs(t - k["gn_pose"][4:]).max() < 1e-12
