@@ -12,6 +12,7 @@
 //   replay_ref pnp <pnp.bin> <out.bin>     the three Ceres PnP solves (GPU) + SelfGaussNewton (host, reference code only)
 //   replay_ref gn  <pnp.bin> <out.bin>     SelfGaussNewton alone: no GPU, no shim — pins the oracle's Gauss-Newton
 //   replay_ref ba  <scene.bin> <out.bin>   SolveWithCeresDynamicAutoDiff (GPU)
+//   replay_ref g2o <scene.bin> <out.bin>   SolveWithG2O (st20-g2o/src/include/test_g2o.h:94-147) as written: vertices / edges -> GPU engine
 //   replay_ref tri <scene.bin> <out.bin>   the per-landmark triangulation solves of sim_data.cpp:298-311: the reference's
 //                                          loop (host LM, Jet autodiff of the reference functor) and the batched extension
 #include <cstdio>
@@ -35,6 +36,7 @@ struct Scene {
 
 #include "solver.hpp"        // -I /root/reference/st17-ceres/src/include
 #include "test_ceres.h"      // -I <build dir>: symlink to /root/reference/st20-g2o/src/include/test_ceres.h
+#include "test_g2o.h"        // same: the g2o comparator, against include/compat/g2o (the g2o-shaped door over the C ABI)
 
 static bool read_all(const char* path, std::vector<char>& buf) {
   FILE* f = fopen(path, "rb");
@@ -121,6 +123,14 @@ static int run_ba(const char* in, const char* out) {
   const int g0 = ceres::internal::gpu_solve_count();
   ns_st20::SolveWithCeresDynamicAutoDiff(dm, true);          // test_ceres.h:98-152, as written
   printf("gpu_solves=%d\n", ceres::internal::gpu_solve_count() - g0);
+  write_state(out, dm);
+  return 0;
+}
+
+static int run_g2o(const char* in, const char* out) {
+  ns_st20::DataManager dm;
+  if (load_scene(in, dm)) return 2;
+  ns_st20::SolveWithG2O(dm, true);          // test_g2o.h:94-147, as written (landmarks are written back, cameras are not: :137-145)
   write_state(out, dm);
   return 0;
 }
@@ -250,6 +260,7 @@ int main(int argc, char** argv) {
   if (argc >= 4 && !strcmp(argv[1], "gn")) return run_pnp(argv[2], argv[3], true);
   if (argc >= 4 && !strcmp(argv[1], "ba")) return run_ba(argv[2], argv[3]);
   if (argc >= 4 && !strcmp(argv[1], "tri")) return run_tri(argv[2], argv[3]);
+  if (argc >= 4 && !strcmp(argv[1], "g2o")) return run_g2o(argv[2], argv[3]);
   fprintf(stderr, "usage: replay_ref pnp|gn|ba|tri <in> <out>\n");
   return 2;
 }

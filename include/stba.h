@@ -256,6 +256,20 @@ int stba_triangulate(int device, int32_t n_cam, int32_t n_lm, int64_t n_obs, con
                      const double* obs_uv, const stba_options* opt, int32_t* iterations,
                      double* final_cost, int32_t* termination, float* kernel_ms);
 
+/* `SelfGaussNewton`, st17-ceres/src/include/solver.hpp:387-462: the reference's hand Gauss-Newton for
+ * one camera against fixed 3-D points — H = sum J^T J (6 x 6), g = -sum J^T r, delta = H.ldlt().solve(g),
+ * R <- R Exp(d_theta), t <- t + d_t, stop at |d_theta| + |d_t| < tolerance (1e-8) or after max_iterations (10).  The
+ * whole loop is ONE kernel; a batch of independent problems (problem p owns observations [ptr[p], ptr[p+1])) runs
+ * one CTA each.  q f64[n,4] xyzw / t f64[n,3]: camera -> world poses, initial guess in, result out.  iterations
+ * receives the loop index at exit (what the reference logs as "iter num"), last_change the last |d_theta| + |d_t|.
+ * jacobian_mode REFERENCE reproduces solver.hpp:195 (e_R without the translation term): same
+ * iterates as the reference; EXACT uses the true derivative. */
+#define STBA_PNP_JACOBIAN_REFERENCE 0
+#define STBA_PNP_JACOBIAN_EXACT 1
+int stba_pnp_gauss_newton(int device, int32_t n_problems, const int32_t* ptr, const double* points,
+                          const double* uv, double* q, double* t, int32_t max_iterations, double tolerance,
+                          int32_t jacobian_mode, int32_t* iterations, double* last_change, float* kernel_ms);
+
 /* ==================================================================================== */
 /* Zhang calibration (BASELINE.json configs[3]).                   */
 /* Corners of all views are concatenated: view v owns [view_ptr[v], view_ptr[v+1]);        */

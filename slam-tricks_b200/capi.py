@@ -120,6 +120,7 @@ SIGNATURES = {
                                   _ip, _ip, _ip, _ip, _dp, _ip]),
     "stba_triangulate": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp, _ip, _ip, _dp, C.POINTER(Options),
                                    _ip, _dp, _ip, C.POINTER(C.c_float)]),
+    "stba_pnp_gauss_newton": (C.c_int, [C.c_int, C.c_int32, _ip, _dp, _dp, _dp, _dp, C.c_int32, C.c_double, C.c_int32, _ip, _dp, C.POINTER(C.c_float)]),
     "stba_calib_initialize": (C.c_int, [C.c_int32, _ip, _dp, _dp, _dp, _dp, _dp]),
     "stba_calib_optimize": (C.c_int, [C.c_int, C.c_int32, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int32, C.c_double, _ip, _dp, _dp, _lp]),
     "stba_calib_optimize_timed": (C.c_int, [C.c_int, C.c_int32, _ip, _dp, _dp, _dp, _dp, _dp, C.c_int32, C.c_double, _ip, _dp, _dp, _lp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

@@ -19,6 +19,6 @@ else
 fi
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr"
 OUT=${OUT:-../libstba.so}
-$NVCC $FLAGS -shared -o $OUT stba_engine.cu stba_chol.cu stba_problem.cu stba_front.cu stba_calib.cu stba_posegraph.cu -I../../include \
+$NVCC $FLAGS -shared -o $OUT stba_engine.cu stba_chol.cu stba_problem.cu stba_front.cu stba_pnp.cu stba_calib.cu stba_posegraph.cu -I../../include \
   $NCCL_FLAGS -L/usr/local/cuda/lib64 -lcusolver -lcublas -Xlinker -rpath,/usr/local/cuda/lib64 "$@"
 echo "built $(readlink -f $OUT)"

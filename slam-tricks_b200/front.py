@@ -42,3 +42,25 @@ def triangulate(cam_q, cam_t, lm0, obs_cam, obs_lm, obs_uv, options=None, device
                                   capi.dptr(uv), C.byref(options) if options is not None else None, capi.iptr(its), capi.dptr(cost),
                                   capi.iptr(term), C.byref(ms)), "stba_triangulate")
     return lm, its, cost, [capi.TERMINATION[int(x)] for x in term], float(ms.value)
+
+
+PNP_JACOBIAN_REFERENCE, PNP_JACOBIAN_EXACT = 0, 1
+
+
+def pnp_gauss_newton(points, uv, q0, t0, ptr=None, max_iterations=10, tolerance=1e-8, jacobian="reference", device=0):
+    """`SelfGaussNewton` (st17-ceres/src/include/solver.hpp:387-462) on the GPU, one kernel for the whole loop.
+    Single problem: points [n,3], uv [n,2], q0 [4], t0 [3].  Batch: pass ptr (i32[n_problems+1]) and q0 [p,4], t0 [p,3].
+    Returns (q, t, iterations, last_change, kernel_ms); `iterations` is the reference's "iter num"."""
+    L = capi.lib()
+    single = ptr is None
+    pts = capi.as_f64(points, (len(points), 3)); uvs = capi.as_f64(uv, (len(uv), 2))
+    ptr = np.ascontiguousarray([0, len(pts)] if single else ptr, dtype=np.int32)
+    n = len(ptr) - 1
+    q = np.array(q0, dtype=np.float64, order="C").reshape(n, 4); t = np.array(t0, dtype=np.float64, order="C").reshape(n, 3)
+    its = np.zeros(n, np.int32); change = np.zeros(n); ms = C.c_float(0)
+    capi.check(L.stba_pnp_gauss_newton(device, n, capi.iptr(ptr), capi.dptr(pts), capi.dptr(uvs), capi.dptr(q), capi.dptr(t), max_iterations, tolerance,
+                                       PNP_JACOBIAN_REFERENCE if jacobian == "reference" else PNP_JACOBIAN_EXACT, capi.iptr(its), capi.dptr(change),
+                                       C.byref(ms)), "stba_pnp_gauss_newton")
+    if single:
+        return q[0], t[0], int(its[0]), float(change[0]), float(ms.value)
+    return q, t, its, change, float(ms.value)

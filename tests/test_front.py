@@ -1,6 +1,7 @@
 """Front of the path: visibility predicate + ordered compaction, batched
 landmark triangulation.  CPU tests pin the oracle; `-m gpu` tests compare the CUDA path with it
 through the C ABI (index work bit-exact, floating point to the tolerances written below)."""
+import os
 import numpy as np
 import pytest
 
@@ -193,3 +194,56 @@ def test_triangulation_config_C(stba):
         x, sm = dense_lm.solve(d["lm"][l], lambda P: fo.triangulation_residual_jacobian(R[d["obs_cam"][s]], tcw[d["obs_cam"][s]], d["obs_uv"][s], P))
         assert len(sm.iterations) == its[l] and np.max(np.abs(x - lm[l])) < 1e-9
     print("triangulate C: %.3f ms kernel, mean iterations %.2f" % (ms, its.mean()))
+
+
+# ---- SelfGaussNewton (st17-ceres/src/include/solver.hpp:387-462) as one kernel ----------------------------------
+def _numpy_gauss_newton(s, q, t, exact, max_it=10, tol=1e-8):
+    from oracle import ba_oracle as bo, lie
+    it = 0
+    for it in range(max_it):
+        H = np.zeros((6, 6)); g = np.zeros(6)
+        R = lie.quat_to_rot(q)
+        for P, uv in zip(s["points"], s["uv"]):
+            pc = R.T @ (P - t)
+            r = pc[:2] / pc[2] - uv
+            e_R, e_t = bo.pnp_reference_jacobian(q, t, P)
+            if exact:
+                iz = 1.0 / pc[2]
+                Pi = np.array([[iz, 0, -pc[0] * iz * iz], [0, iz, -pc[1] * iz * iz]])
+                e_R = Pi @ lie.hat(pc)
+            J = np.concatenate([e_R, e_t], axis=1)
+            H += J.T @ J; g -= J.T @ r
+        d = np.linalg.solve(H, g)
+        q = lie.so3_plus(q, d[:3]); t = t + d[3:]
+        if np.linalg.norm(d[:3]) + np.linalg.norm(d[3:]) < tol:
+            break
+    return q, t, it
+
+
+@pytest.mark.gpu
+def test_pnp_gauss_newton_kernel_equals_the_reference_self_gauss_newton(stba):
+    s = stba.synth.pnp_scene()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_kat.npz"))
+    # (1) reference Jacobian form: same "iter num" and pose as SelfGaussNewton run from the reference source
+    q, t, its, change, ms = stba.front.pnp_gauss_newton(s["points"], s["uv"], s["q_init"], s["t_init"])
+    assert its == int(z["gn_iter_num"]) and change < 1e-8 and ms > 0
+    assert min(np.abs(q - z["gn_pose"][:4]).max(), np.abs(q + z["gn_pose"][:4]).max()) < 1e-12 and np.abs(t - z["gn_pose"][4:]).max() < 1e-12
+    # ... and as the oracle's restatement, iteration by iteration (capped runs)
+    for cap in (1, 2, 3, 5):
+        qg, tg, ig, _, _ = stba.front.pnp_gauss_newton(s["points"], s["uv"], s["q_init"], s["t_init"], max_iterations=cap)
+        qo, to, _ = _numpy_gauss_newton(s, s["q_init"].copy(), s["t_init"].copy(), exact=False, max_it=cap)
+        assert ig == cap and np.abs(qg - qo).max() < 1e-12 and np.abs(tg - to).max() < 1e-12
+    # (2) exact Jacobian: also the published pose, in no more iterations
+    q2, t2, its2, _, _ = stba.front.pnp_gauss_newton(s["points"], s["uv"], s["q_init"], s["t_init"], jacobian="exact")
+    qo, to, io = _numpy_gauss_newton(s, s["q_init"].copy(), s["t_init"].copy(), exact=True)
+    assert its2 == io and np.abs(q2 - qo).max() < 1e-12 and np.abs(t2 - to).max() < 1e-12
+    assert min(np.abs(q2 - s["q_real"]).max(), np.abs(q2 + s["q_real"]).max()) < 1e-8 and np.abs(t2 - s["t_real"]).max() < 1e-8
+    # (3) a batch: the same problem three times from three initial guesses, ragged observation counts
+    n = len(s["points"])
+    pts = np.concatenate([s["points"], s["points"][:n - 3], s["points"]]); uvs = np.concatenate([s["uv"], s["uv"][:n - 3], s["uv"]])
+    ptr = np.array([0, n, 2 * n - 3, 3 * n - 3], np.int32)
+    q0 = np.stack([s["q_init"], s["q_init"], z["gn_pose"][:4]]); t0 = np.stack([s["t_init"], s["t_init"] + 0.1, z["gn_pose"][4:]])
+    qb, tb, ib, cb, _ = stba.front.pnp_gauss_newton(pts, uvs, q0, t0, ptr=ptr)
+    assert np.abs(qb[0] - q).max() < 1e-15 and ib[0] == its and ib[2] <= 1
+    for k in range(3):
+        assert min(np.abs(qb[k] - s["q_real"]).max(), np.abs(qb[k] + s["q_real"]).max()) < 1e-7 and np.abs(tb[k] - s["t_real"]).max() < 1e-7
