@@ -853,7 +853,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 //     inverts the 32 x 32 diagonal factor blocks as they appear and publishes them (pinv): the consumers of
 //     the panel (the solve of the next tile row) start on block column b while b + 1 is being factored.
 constexpr int QLD = NB + 4;      // (q QLD + g) mod 16 distinct over a half-warp: conflict-free DMMA fragments
-constexpr int PROG_SMEM = (NB * QLD + NB + 64) * (int)sizeof(double);
+constexpr int PROG_SMEM = (NB * QLD + NB + 32 * 32) * (int)sizeof(double);
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 480;" ::: "memory"); }
 
@@ -869,10 +869,10 @@ __device__ __forceinline__ double fast_rcp(double d) {
 
 __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv,
                                                   int* __restrict__ info, double* sm, int* pb_flag, int* pinv_flag,
-                                                  volatile int* s_sig) {
+                                                  volatile int* s_sig, volatile int* s_prog) {
   double* D = sm;                  // D[c * QLD + r], lower triangle
   double* xd = sm + NB * QLD;      // 1 / L_jj
-  double* cb = xd + NB;            // 2 x 32 column exchange buffers of the pivot warp
+  double* cb = xd + NB;            // 32 x 32: column j of the pivot block as it was when it became the pivot column
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   TICK(0);
@@ -896,7 +896,7 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
       D[c * QLD + r2 + 1] = x1;
     }
   }
-  if (tid == 0) *s_sig = 0;
+  if (tid == 0) { *s_sig = 0; *s_prog = 0; }
   __syncthreads();
   TICK(1);
   if (warp == 15) {
@@ -904,6 +904,7 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
     for (int b = 0; b < 4; ++b) {
       const int b0 = 32 * b;
       while (*s_sig < b + 1) { }
+      __threadfence_block();
       __syncwarp();
       double x[32];
 #pragma unroll
@@ -929,64 +930,94 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
   } else {
     for (int b = 0; b < 4; ++b) {
       const int b0 = 32 * b;
-      if (warp == 0) {
-        // (1) pivot chain: lane = row; column j is exchanged through shared memory (shuffles in this
-        //     warp-specialised branch compile to WARPSYNC.COLLECTIVE sequences)
+      const int base = 64 * b;       // *s_prog = base + number of complete columns of cb; base + 33: xd is complete too
+      if (warp == b) {
+        // (1) pivot chain, rows b0 .. b0 + 31: lane = row.  Column j + 1 is exchanged (shared memory) one dependent
+        //     operation after the reciprocal of pivot j; the rest of the rank-1 update of step j is issued inside
+        //     step j + 1, where it fills the latency of the exchange and of the reciprocal (84 cycles of
+        //     dependent latency per pivot: tools/ubench/potf2.cu measures 137 for this loop, 243 for the
+        //     plain one).  Branch-free: the pivots are checked once after the loop.
         double a[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? D[(b0 + c) * QLD + b0 + lane] : 0.0;
-        bool bad = false;
         cb[lane] = a[0];
+        __threadfence_block();
         __syncwarp();
+        if (lane == 0) *s_prog = base + 1;
+        double tp = 0.0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const double* col = cb + (j & 1) * 32;
+          const double* col = cb + j * 32;
           const double d = col[j];
-          if (!(d > 0.0) && !bad) { bad = true; if (lane == 0 && b0 + j < nb) atomicCAS(info, 0, k0 + b0 + j + 1); }
-          const double u = (j + 1 < 32) ? a[j] * col[j + 1] : 0.0;   // beside the reciprocal chain
+          const double nx = (j + 1 < 32) ? col[j + 1] : 0.0;
+          if (j > 0) {
+            const double* pc = cb + (j - 1) * 32;
+#pragma unroll
+            for (int k = j + 2; k < 32; ++k) a[k] = fma(-tp, pc[k], a[k]);
+          }
+          const double u = a[j] * nx;
           const double r = fast_rcp(d);
           if (j + 1 < 32) {
-            a[j + 1] = fma(-u, r, a[j + 1]);             // one dependent operation after 1 / d
-            cb[((j + 1) & 1) * 32 + lane] = a[j + 1];   // next column out before the rest of the update
+            a[j + 1] = fma(-u, r, a[j + 1]);
+            cb[(j + 1) * 32 + lane] = a[j + 1];
+            if ((j & 3) == 3 || j == 30) __threadfence_block();
+            __syncwarp();
+            if (((j & 3) == 3 || j == 30) && lane == 0) *s_prog = base + j + 2;      // the followers advance four columns at a time
           }
-          const double t = a[j] * r;                     // a_ij / d_j
-#pragma unroll
-          for (int k = j + 2; k < 32; ++k) a[k] = fma(-t, col[k], a[k]);
-          const double rs = fast_rsqrt(d);               // beside the chain: scales column j
-          a[j] = (lane == j) ? d * rs : a[j] * rs;
-          if (lane == j) xd[b0 + j] = rs;
-          __syncwarp();
+          tp = a[j] * r;
+          if (j + 2 < 32) a[j + 2] = fma(-tp, col[j + 2], a[j + 2]);
         }
+        // scale: L_ij = a_ij / sqrt(d_j); lane j owns pivot j
+        const double dl = cb[lane * 32 + lane];
+        const unsigned badm = __ballot_sync(FULL, !(dl > 0.0) && b0 + lane < nb);
+        if (badm && lane == 0) atomicCAS(info, 0, k0 + b0 + __ffs(badm));
+        const double rsl = fast_rsqrt(dl);
+        xd[b0 + lane] = rsl;
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *s_prog = base + 33;
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c <= lane) D[(b0 + c) * QLD + b0 + lane] = a[c];
+        for (int c = 0; c < 32; ++c) {
+          const double v = (c == lane) ? dl * rsl : a[c] * xd[b0 + c];
+          if (c <= lane) D[(b0 + c) * QLD + b0 + lane] = v;
+        }
         __threadfence_block();
         __syncwarp();
         if (lane == 0) *s_sig = b + 1;
         TICK(20 + b);
+      } else if (warp > b && warp < 4) {
+        // (2) rows below the pivot block follow the same elimination, four columns behind at most: the former
+        //     forward substitution of these rows (a separate phase on the chain) is gone
+        const int r = 32 * warp + lane;
+        double a[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a[c] = D[(b0 + c) * QLD + r];
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const int need = base + (j4 + 4 < 32 ? j4 + 4 : 32);
+          while (*s_prog < need) { }
+          __threadfence_block();
+          double rc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rc[u] = fast_rcp(cb[(j4 + u) * 32 + j4 + u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j4 + u;
+            const double* col = cb + j * 32;
+            const double t = a[j] * rc[u];
+#pragma unroll
+            for (int k = j + 1; k < 32; ++k) a[k] = fma(-t, col[k], a[k]);
+          }
+        }
+        while (*s_prog < base + 33) { }
+        __threadfence_block();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) D[(b0 + c) * QLD + r] = a[c] * xd[b0 + c];
       }
       bar_workers();
       TICK(2 + 3 * b);
-      // (2) rows below the sub-block: x L_bb^T = a by forward substitution, one thread per row
-      const int below = NB - b0 - 32;
-      if (tid < below) {
-        const int r = b0 + 32 + tid;
-        double sr[32];
-#pragma unroll
-        for (int p = 0; p < 32; ++p) sr[p] = D[(b0 + p) * QLD + r];
-#pragma unroll
-        for (int p = 0; p < 32; ++p) {
-          const double x = sr[p] * xd[b0 + p];
-          sr[p] = x;
-          const double* lp = D + (b0 + p) * QLD + b0;
-#pragma unroll
-          for (int c = p + 1; c < 32; ++c) sr[c] = fma(-x, lp[c], sr[c]);
-        }
-#pragma unroll
-        for (int p = 0; p < 32; ++p) D[(b0 + p) * QLD + r] = sr[p];
-      }
-      bar_workers();
       TICK(3 + 3 * b);
+      const int below = NB - b0 - 32;
       if (warp == 14) {
         // block column b is final: copy it out and publish it
         for (int c = b0; c < b0 + 32 && c < nb; ++c) {
@@ -1002,9 +1033,9 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
         __syncwarp();
         if (lane == 0) st_release_gpu(pb_flag, b + 1);
       } else if (below > 0) {
-        // (3) rank-32 update of the remaining lower triangle on the FP64 tensor pipe: 8 x 8 tiles over warps 0..13
-        // 16 x 16 macro tiles (four independent accumulator pairs hide the DMMA latency), lower triangle
-        // of the (below / 16)^2 grid dealt round-robin to the 14 warps
+        // (3) rank-32 update of the remaining lower triangle on the FP64 tensor pipe: 16 x 16 macro tiles (four
+        //     independent accumulator pairs hide the DMMA latency), lower triangle of the (below / 16)^2 grid
+        //     dealt round-robin to the 14 warps
         const int nt = below / 16;
         int cnt = 0;
         for (int ti = 0; ti < nt; ++ti)
@@ -1585,6 +1616,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag(const DagParams P) 
   __shared__ int4 s_task;
   __shared__ int s_ok;
   __shared__ int s_sig;
+  __shared__ int s_prog;
   const int tid = threadIdx.x, b = blockIdx.x;
   const int T = P.T;
   int* pdone = P.flags + F_PDONE;
@@ -1646,7 +1678,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag(const DagParams P) 
       const long long c0 = clock64();
       {
         int* pb = P.flags + F_PDONE + T + P.R64 * T;
-        potrf128_prog_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, P.info, sm, pb + k, pb + T + k, &s_sig);
+        potrf128_prog_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, P.info, sm, pb + k, pb + T + k, &s_sig, &s_prog);
       }
       __threadfence();
       __syncthreads();
