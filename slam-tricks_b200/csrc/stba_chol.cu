@@ -1746,6 +1746,585 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag(const DagParams P) 
 #undef n_tasks
 }
 
+// =================================================================================================
+// DAG kernel, second scheduler (default): the same tile operations, but
+//   * no queues: every worker SCANS a table of tile states (st[i][j] = block-column updates applied to tile
+//     (i, j), sv[h] = block columns for which the 64-row half h holds final L) and claims, with one
+//     compare-and-swap, the ready task NEAREST THE FACTORISATION FRONT: panel solves first, then updates of
+//     block column npan, npan + 1, ...  An update takes every panel that is available for its tile (up to G),
+//     so tiles near the front are served one panel at a time with minimal latency while far tiles collect
+//     their updates lazily with a long K (one C-tile round trip per G panels).  The FIFO queues of the first
+//     scheduler tied the front to the bulk: potrf(k) could never run more than W + 2 panels ahead of the
+//     far queue, so the chain-bound and the throughput-bound phases added up instead of overlapping
+//     (profiles/r2_dense_notes.md).
+//   * five dedicated CTAs carry the chain:  0 = potrf(k);  1 = solve of tile row k+1;  2 = update of the
+//     diagonal tile (k+1, k+1) with panel k;  3 = solve of tile row k+2;  4 = update of tile (k+2, k+1) with
+//     panel k.  CTAs 1 and 3 follow CTA 0 block column by block column (pb / pinv), CTAs 2 and 4 follow the
+//     solves the same way (xpub): when potrf(k) ends, a quarter of a solve and a rank-32 update are left.
+// Each (tile, panel) pair and each (half, panel) solve is executed exactly once; the work units finished
+// are counted in F2_DONE and the workers leave when the count reaches the total.
+// =================================================================================================
+enum { F2_ABORT = 0, F2_NPAN = 32, F2_DONE = 64, F2_JMIN = 96, F2_ARR = 128 };     // F2_JMIN: every column before it is complete (hint, monotone)
+constexpr int ST_LOCK = 1 << 20;
+enum { TASK2_EXIT = -1, TASK2_TRSM = 0, TASK2_UPD = 1, TASK2_INV = 2 };
+
+struct Dag2Params {
+  double* S;
+  int ld, n, n_rows, T, Tr, R64;
+  double* Linv;
+  int* info;
+  int* flags;               // [F2_ABORT] [F2_NPAN] [F2_DONE] . pdone[T] pb[T] pinv[T] invst[T] xpub[Tr] sv[R64] st[Tr * T]
+  int total_units;
+  int W, G;
+  const int* tiles;         // every tile (i | j << 16), column by column
+  const int* col_start;     // col_start[j]: position of tile (j, j) in tiles[]
+  int n_tiles;
+  unsigned long long* trace;
+  long long* prof;
+};
+__device__ __forceinline__ int* f2_pdone(const Dag2Params& P) { return P.flags + F2_ARR; }
+__device__ __forceinline__ int* f2_pb(const Dag2Params& P) { return f2_pdone(P) + P.T; }
+__device__ __forceinline__ int* f2_pinv(const Dag2Params& P) { return f2_pb(P) + P.T; }
+__device__ __forceinline__ int* f2_invst(const Dag2Params& P) { return f2_pinv(P) + P.T; }
+__device__ __forceinline__ int* f2_xpub(const Dag2Params& P) { return f2_invst(P) + P.T; }
+__device__ __forceinline__ int* f2_sv(const Dag2Params& P) { return f2_xpub(P) + P.Tr; }
+__device__ __forceinline__ int* f2_st(const Dag2Params& P) { return f2_sv(P) + P.R64; }
+__device__ __forceinline__ bool half2_exists(const Dag2Params& P, int h) { return h * 64 < P.n_rows; }
+
+__device__ __forceinline__ void dag2_abort(const Dag2Params& P) {
+  atomicCAS(P.info, 0, -1);
+  st_release_gpu(P.flags + F2_ABORT, 1);
+}
+
+// CTA-wide wait until *f0 >= v0 (and *f1 >= v1).  Thread 0 polls with relaxed loads and repeats the successful
+// observation as an acquire load.  Returns false after an abort.
+__device__ __forceinline__ bool wait2(const Dag2Params& P, const int* f0, int v0, const int* f1, int v1, int* s_ok, long long* t_wait) {
+  if (threadIdx.x == 0) {
+    const long long c0 = clock64();
+    long long spins = 0;
+    int ok = 1;
+    for (;;) {
+      const int a = ld_relaxed(f0) & ~ST_LOCK, b = f1 ? (ld_relaxed(f1) & ~ST_LOCK) : v1;
+      if (a >= v0 && b >= v1) {
+        ld_acquire_gpu(f0);
+        if (f1) ld_acquire_gpu(f1);
+        break;
+      }
+      if ((++spins & 255) == 0 && ld_relaxed(P.flags + F2_ABORT)) { ok = 0; break; }
+      if (spins > SPIN_LIMIT) { dag2_abort(P); ok = 0; break; }
+    }
+    *s_ok = ok;
+    *t_wait += clock64() - c0;
+  }
+  __syncthreads();
+  const int ok = *s_ok;
+  __syncthreads();
+  return ok != 0;
+}
+
+// CTA-wide wait until min(*f0, *f1) >= v; returns that minimum as thread 0 saw it (acquire), -1 after an abort.
+__device__ __forceinline__ int wait2v(const Dag2Params& P, const int* f0, const int* f1, int v, int* s_ok, long long* t_wait) {
+  if (threadIdx.x == 0) {
+    const long long c0 = clock64();
+    long long spins = 0;
+    int ok = -1;
+    for (;;) {
+      if (min(ld_relaxed(f0), ld_relaxed(f1)) >= v) {
+        ok = min(ld_acquire_gpu(f0), ld_acquire_gpu(f1));
+        break;
+      }
+      if ((++spins & 255) == 0 && ld_relaxed(P.flags + F2_ABORT)) break;
+      if (spins > SPIN_LIMIT) { dag2_abort(P); break; }
+    }
+    *s_ok = ok;
+    *t_wait += clock64() - c0;
+  }
+  __syncthreads();
+  const int ok = *s_ok;
+  __syncthreads();
+  return ok;
+}
+
+// ---- solve of one tile row against panel k, following CTA 0 block column by block column ----------------
+// X = A(i, k) L_kk^-T by forward substitution over the four 32-column blocks as they are published (pb / pinv),
+// each warp carrying 8 of the 128 rows (warp-private strips: no CTA-wide synchronisation inside a step).  Every
+// finished block column is published (xpub[i] = 4 k + b + 1) for the update CTAs; at the end the two halves of
+// the tile row are marked solved for block column k.
+__device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k, double* sm, int* s_ok, long long* prof, int trace_base) {
+  const int T = P.T, ld = P.ld, n_rows = P.n_rows;
+  double* __restrict__ S = P.S;
+  const int r0 = i * NB, k0 = k * NB, nb = min(NB, P.n - k0);
+  const bool h2 = half2_exists(P, 2 * i + 1);
+  const double* Linv = P.Linv + (size_t)k * NB * NB;
+  double* Xs = sm;                        // Xs[(strip * NB + col) * 8 + row_in_strip]
+  double* Lb = sm + 16 * NB * 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  int* sv = f2_sv(P);
+  if (trace_base >= 0) TRACE(P, k, trace_base);
+  // tile (i, k) has received every update (panels 0 .. k-1)
+  if (!wait2(P, f2_st(P) + (size_t)i * T + k, k, nullptr, 0, s_ok, prof)) return false;
+  if (trace_base >= 0) TRACE(P, k, trace_base + 1);
+  const long long c_begin = clock64();
+  for (int c = warp; c < NB; c += 16) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int r2 = 2 * lane + 64 * s, row = r0 + r2;
+      double* dst = Xs + ((r2 >> 3) * NB + c) * 8 + (r2 & 7);
+      const double* src = S + (size_t)(k0 + c) * ld + row;
+      if (c < nb && row + 1 < n_rows) {
+        cp_async16(dst, src, true);
+      } else {
+        dst[0] = (c < nb && row < n_rows) ? __ldcg(src) : 0.0;
+        dst[1] = 0.0;
+      }
+    }
+  }
+  cp_async_commit();
+  double* Xw = Xs + warp * NB * 8;
+  const int row = r0 + warp * 8 + g;
+  int loaded = 0;                  // block columns of L_kk already requested
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (loaded <= j) {
+      // (the count must be CTA-uniform: every thread derives its loads and the next wait from it)
+      const int avail = wait2v(P, f2_pb(P) + k, f2_pinv(P) + k, j + 1, s_ok, prof);
+      if (avail < 0) return false;
+      for (int jb = loaded; jb < min(avail, 4); ++jb) {
+        double* Lj = Lb + tu_lb_off(jb);
+        const int ldj = tu_lb_ld(jb);
+        for (int cl = warp; cl < 32; cl += 16) {
+          const int c = 32 * jb + cl;
+          double* dl = Lj + cl * ldj - 32 * jb;           // dl[r] = L(r, c), r >= 32 jb
+          const bool col_ok = c < nb;
+          for (int r2 = 32 * jb + 2 * lane; r2 < NB; r2 += 64) {
+            const bool in_diag = r2 < 32 * jb + 32;
+            const double* src = in_diag ? Linv + (size_t)c * NB + r2 : S + (size_t)(k0 + c) * ld + k0 + r2;
+            if (col_ok && r2 >= c && r2 + 1 < nb) {
+              cp_async16(dl + r2, src, true);
+            } else {
+              dl[r2] = (col_ok && r2 >= c && r2 < nb) ? __ldcg(src) : 0.0;
+              dl[r2 + 1] = (col_ok && r2 + 1 >= c && r2 + 1 < nb) ? __ldcg(src + 1) : 0.0;
+            }
+          }
+        }
+      }
+      loaded = min(avail, 4);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    if (trace_base >= 0) TRACE(P, k, trace_base + 2 + j);
+    {
+      double a4[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) a4[nt][e] = Xw[(32 * j + 8 * nt + 2 * q + e) * 8 + g];
+#pragma unroll
+      for (int p = 0; p < j; ++p) {
+        const double* Lp = Lb + tu_lb_off(p) + (32 * j - 32 * p) + g;
+        const int ldp = tu_lb_ld(p);
+#pragma unroll
+        for (int kk = 0; kk < 32; kk += 4) {
+          const double a = -Xw[(32 * p + kk + q) * 8 + g];
+          const double* bs = Lp + (kk + q) * ldp;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma(a4[nt][0], a4[nt][1], a, bs[nt * 8]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) Xw[(32 * j + 8 * nt + 2 * q + e) * 8 + g] = a4[nt][e];
+      __syncwarp();
+      double out[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+      const double* Ij = Lb + tu_lb_off(j) + g;
+      const int ldj = tu_lb_ld(j);
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+        const double a = Xw[(32 * j + kk + q) * 8 + g];
+        const double* bs = Ij + (kk + q) * ldj;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma(out[nt][0], out[nt][1], a, bs[nt * 8]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 32 * j + 8 * nt + 2 * q + e;
+          Xw[c * 8 + g] = out[nt][e];
+          if (row < n_rows && c < nb) S[(size_t)(k0 + c) * ld + row] = out[nt][e];
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      st_release_gpu(f2_xpub(P) + i, 4 * k + j + 1);
+      if (j == 3) {      // the tile row is solved for block column k
+        st_release_gpu(sv + 2 * i, k + 1);
+        if (h2) st_release_gpu(sv + 2 * i + 1, k + 1);
+        if (trace_base >= 0) TRACE(P, k, trace_base + 6);
+      }
+    }
+  }
+  if (tid == 0) { prof[2] += clock64() - c_begin; prof[5] += 1; }
+  return true;
+}
+
+// ---- update of one near-diagonal tile with panel k, following the solves block column by block column ----
+// C(i, j) -= X_i X_j^T where X_i = L(i, k), X_j = L(j, k) are being produced by the solve CTAs: the
+// accumulators hold the C tile while the four rank-32 updates arrive (xpub).  16 warps, 4 x 4, warp tile 32 x 32;
+// on a diagonal tile only the warp tiles on or below the diagonal work (same map as upd_dev).
+constexpr int US_LD = NB + 4;
+constexpr int US_SMEM = cmax(2 * 32 * US_LD, NB * LDC) * (int)sizeof(double);
+__device__ __forceinline__ bool upd_stream_dev(const Dag2Params& P, int i, int j, int k, double* smem, int* s_ok, long long* prof,
+                                               unsigned long long* cbar, unsigned& cphase, int trace_slot) {
+  const int T = P.T, lda = P.ld, n_rows = P.n_rows, n_cols = P.n;
+  double* __restrict__ S = P.S;
+  const int i0 = i * NB, j0 = j * NB, k0 = k * NB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  const bool diag = i == j;
+  int wm = warp >> 2, wn = warp & 3;
+  bool active = true;
+  if (diag) {
+    active = warp < 10;
+    switch (warp) {
+      case 0: wm = 0; wn = 0; break;  case 1: wm = 1; wn = 0; break;  case 2: wm = 1; wn = 1; break;  case 3: wm = 2; wn = 0; break;
+      case 4: wm = 2; wn = 1; break;  case 5: wm = 2; wn = 2; break;  case 6: wm = 3; wn = 0; break;  case 7: wm = 3; wn = 1; break;
+      case 8: wm = 3; wn = 2; break;  case 9: wm = 3; wn = 3; break;  default: wm = 0; wn = 0; break;
+    }
+  }
+  // the tile has received every update the workers owe it (panels 0 .. k-1)
+  int* st = f2_st(P) + (size_t)i * T + j;
+  if (!wait2(P, st, k, nullptr, 0, s_ok, prof)) return false;
+  const long long c_begin = clock64();
+  double acc[4][4][2];
+  {
+    const int ncol = min(NB, n_cols - j0);
+    const unsigned col_bytes = (unsigned)min(NB, lda - i0) * 8u;
+    if (tid == 0) mbar_expect_tx(cbar, col_bytes * (unsigned)ncol);
+    __syncthreads();
+    if (tid < ncol) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bulk_g2s(smem + tid * LDC, S + (size_t)(j0 + tid) * lda + i0, col_bytes, cbar);
+    }
+    mbar_wait(cbar, cphase & 1);
+    ++cphase;
+    if (active) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) acc[mt][nt][e] = smem[(wn * 32 + nt * 8 + 2 * q + e) * LDC + wm * 32 + mt * 8 + g];
+    }
+    __syncthreads();
+  }
+  double* As = smem;                     // [32][US_LD]
+  double* Bs = smem + 32 * US_LD;
+  const int* xi = f2_xpub(P) + i;
+  const int* xj = f2_xpub(P) + j;
+  for (int b = 0; b < 4; ++b) {
+    if (!wait2(P, xi, 4 * k + b + 1, diag ? nullptr : xj, 4 * k + b + 1, s_ok, prof)) return false;
+    // 32 columns x 128 rows of both operands
+#pragma unroll
+    for (int p = 0; p < 32 * 64 / DAG_THREADS; ++p) {
+      const int piece = tid + p * DAG_THREADS;
+      const int kk = piece >> 6, r2 = (piece & 63) * 2;
+      const int kc = 32 * b + kk;
+      const bool kin = k0 + kc < n_cols;
+      const int ra = i0 + r2, rb = j0 + r2;
+      const double* colp = S + (size_t)(kin ? k0 + kc : k0) * lda;
+      cp_async16(As + kk * US_LD + r2, colp + (ra < n_rows ? ra : 0), kin && ra < n_rows);
+      if (!diag) cp_async16(Bs + kk * US_LD + r2, colp + (rb < n_rows ? rb : 0), kin && rb < n_rows);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (active) {
+      const double* as = As + wm * 32 + g;
+      const double* bs = (diag ? As : Bs) + wn * 32 + g;
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+        double a[4], bb[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) a[mt] = -as[(kk + q) * US_LD + mt * 8];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) bb[nt] = bs[(kk + q) * US_LD + nt * 8];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], bb[nt]);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      const int r = i0 + wm * 32 + mt * 8 + g;
+      if (r >= n_rows) continue;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = j0 + wn * 32 + nt * 8 + 2 * q + e;
+          if (c < n_cols) S[(size_t)c * lda + r] = acc[mt][nt][e];
+        }
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    st_release_gpu(st, k + 1);
+    TRACE(P, k, trace_slot);
+    prof[3] += clock64() - c_begin;
+    prof[5] += 1;
+  }
+  __syncthreads();
+  return true;
+}
+
+// ---- worker scheduling: warp 0 scans the state tables and claims the ready task nearest the front ----------
+// Returns (type, h | i, j, a | nk << 16): TRSM of half h against panel a; UPD of tile (i, j) with panels a .. a + nk - 1.
+// tiles[] lists every tile (i | j << 16) column by column (the scan order = distance from the front), col_start[j]
+// the position of tile (j, j).  Four candidates per lane and round: the state loads of 128 tiles fly together.
+constexpr int MAX_TR = 256;
+__device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long long* t_wait, int* s_rowsv) {
+  const int lane = threadIdx.x & 31;
+  const int T = P.T, Tr = P.Tr;
+  int* sv = f2_sv(P);
+  int* st = f2_st(P);
+  int* invst = f2_invst(P);
+  const long long c0 = clock64();
+  long long spins = 0;
+  int4 res = make_int4(TASK2_EXIT, 0, 0, 0);
+  for (;;) {
+    if (ld_relaxed(P.flags + F2_ABORT)) break;
+    const int np = ld_relaxed(P.flags + F2_NPAN);
+    bool claimed = false;
+    // ---- solved counts of every tile row; panel solves (tile rows k + 1 and k + 2 belong to CTAs 1 and 3) ----
+    for (int i0 = 0; i0 < Tr; i0 += 32) {
+      const int i = i0 + lane;
+      int ka = 0, kb = 0;
+      bool ok0 = false, ok1 = false;
+      if (i < Tr) {
+        ka = ld_relaxed(sv + 2 * i);
+        const bool h1 = half2_exists(P, 2 * i + 1);
+        kb = h1 ? ld_relaxed(sv + 2 * i + 1) : (1 << 19);
+        s_rowsv[i] = min(ka & ~ST_LOCK, kb & ~ST_LOCK);
+        const bool c0k = !(ka & ST_LOCK) && ka < np && ka + 3 <= i;
+        const bool c1k = h1 && !(kb & ST_LOCK) && kb < np && kb + 3 <= i;
+        const int s0 = c0k ? ld_relaxed(st + (size_t)i * T + ka) : -1;
+        const int s1 = c1k ? ld_relaxed(st + (size_t)i * T + kb) : -1;
+        ok0 = c0k && s0 == ka;
+        ok1 = c1k && s1 == kb;
+      }
+      if (claimed) continue;
+      const unsigned m = __ballot_sync(FULL, ok0 || ok1);
+      if (m) {
+        const int cnt = __popc(m);
+        const int pick = __fns(m, 0, 1 + (wid % cnt));
+        int got = 0, hh = 0, kk = 0;
+        if (lane == pick) {
+          if (ok0 && atomicCAS(sv + 2 * i, ka, ka | ST_LOCK) == ka) { got = 1; hh = 2 * i; kk = ka; }
+          else if (ok1 && atomicCAS(sv + 2 * i + 1, kb, kb | ST_LOCK) == kb) { got = 1; hh = 2 * i + 1; kk = kb; }
+        }
+        got = __shfl_sync(FULL, got, pick);
+        if (got) {
+          res = make_int4(TASK2_TRSM, __shfl_sync(FULL, hh, pick), 0, __shfl_sync(FULL, kk, pick) | (1 << 16));
+          claimed = true;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- updates, from the front outwards.  Columns within W of the front take whatever is available; farther
+    //      columns wait for a full chunk of G panels; if nothing qualifies the first ready far tile is taken
+    //      anyway (better than idling).
+    if (!claimed) {
+      int fb_i = -1, fb_j = 0, fb_a = 0, fb_nk = 0;
+      // Columns behind the front can still owe updates (potrf(j) only needs tile (j, j)): the scan starts at the
+      // first column not known to be complete and moves that hint forward as it goes.
+      const int j_start = min(ld_relaxed(P.flags + F2_JMIN), T);
+      int jinc = 1 << 20;
+      int c0 = P.col_start[j_start];
+      for (; c0 < P.n_tiles && !claimed; c0 += 128) {
+        int ti[4], tj[4], ta[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + 32 * u + lane;
+          const int e = c < P.n_tiles ? __ldg(P.tiles + c) : -1;
+          ti[u] = e < 0 ? -1 : (e & 0xffff);
+          tj[u] = e < 0 ? 0 : (e >> 16);
+          ta[u] = e < 0 ? ST_LOCK : ld_relaxed(st + (size_t)ti[u] * T + tj[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = ti[u], j = tj[u];
+          if (i >= 0 && (ta[u] & ~ST_LOCK) < ((i - j <= 1) ? j - 1 : j)) jinc = min(jinc, j);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (claimed) break;
+          bool ok = false, fb = false;
+          int nk = 0;
+          const int i = ti[u], j = tj[u], a = ta[u];
+          if (i >= 0 && !(a & ST_LOCK)) {
+            const int lim = (i - j <= 1) ? j - 1 : j;      // the last panel of tiles (j, j) and (j+1, j) belongs to CTAs 2 and 4
+            const int av = min(min(s_rowsv[i], s_rowsv[j]), lim);
+            nk = min(av - a, P.G);
+            if (nk > 0) {
+              ok = (j <= np + P.W) || nk == P.G;
+              fb = !ok;
+            }
+          }
+          const unsigned m = __ballot_sync(FULL, ok);
+          if (m) {
+            const int cnt = __popc(m);
+            const int pick = __fns(m, 0, 1 + (wid % cnt));
+            int got = 0;
+            if (lane == pick) got = (atomicCAS(st + (size_t)i * T + j, a, a | ST_LOCK) == a);
+            got = __shfl_sync(FULL, got, pick);
+            if (got) {
+              res = make_int4(TASK2_UPD, __shfl_sync(FULL, i, pick), __shfl_sync(FULL, j, pick), __shfl_sync(FULL, a, pick) | (__shfl_sync(FULL, nk, pick) << 16));
+              claimed = true;
+            }
+          } else if (fb_i < 0) {
+            const unsigned mf = __ballot_sync(FULL, fb);
+            if (mf) {
+              const int pick = __fns(mf, 0, 1 + (wid % __popc(mf)));
+              fb_i = __shfl_sync(FULL, i, pick); fb_j = __shfl_sync(FULL, j, pick); fb_a = __shfl_sync(FULL, a, pick); fb_nk = __shfl_sync(FULL, nk, pick);
+            }
+          }
+        }
+      }
+      {
+        // every tile before position c0 has been looked at: the hint may move up to the first incomplete column seen
+        const int j_unseen = c0 < P.n_tiles ? (__ldg(P.tiles + c0) >> 16) : T;
+        const int j_new = min(__reduce_min_sync(FULL, jinc), j_unseen);
+        if (lane == 0 && j_new > j_start) atomicMax(P.flags + F2_JMIN, j_new);
+      }
+      if (!claimed && fb_i >= 0) {
+        int got = 0;
+        if (lane == 0) got = (atomicCAS(st + (size_t)fb_i * T + fb_j, fb_a, fb_a | ST_LOCK) == fb_a);
+        got = __shfl_sync(FULL, got, 0);
+        if (got) { res = make_int4(TASK2_UPD, fb_i, fb_j, fb_a | (fb_nk << 16)); claimed = true; }
+      }
+    }
+    // ---- completion of the diagonal inverses (needed by the backward substitution only) ----
+    for (int k0 = 0; k0 < np && !claimed; k0 += 32) {
+      const int k = k0 + lane;
+      const bool ok = k < np && ld_relaxed(invst + k) == 0;
+      const unsigned m = __ballot_sync(FULL, ok);
+      if (m) {
+        const int pick = __ffs(m) - 1;
+        int got = 0;
+        if (lane == pick) got = (atomicCAS(invst + k, 0, 1) == 0);
+        got = __shfl_sync(FULL, got, pick);
+        if (got) { res = make_int4(TASK2_INV, 0, 0, (k0 + pick) | (1 << 16)); claimed = true; }
+      }
+    }
+    if (claimed) break;
+    if (ld_relaxed(P.flags + F2_DONE) >= P.total_units) break;
+    if (++spins > (SPIN_LIMIT >> 3)) { if (lane == 0) dag2_abort(P); break; }
+    __nanosleep(200);
+  }
+  __threadfence();
+  if (lane == 0) *t_wait += clock64() - c0;
+  return res;
+}
+
+__global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag2(const Dag2Params P) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int4 s_task;
+  __shared__ int s_ok;
+  __shared__ int s_sig;
+  __shared__ int s_prog;
+  __shared__ unsigned long long s_cbar;
+  __shared__ long long s_prof[16];      // [0] wait [1] potrf [2] trsm [3] upd [4] inv [5] tasks [6] start, [8..11] upd phases
+  __shared__ int s_rowsv[MAX_TR];
+  const int tid = threadIdx.x, b = blockIdx.x;
+  const int T = P.T;
+  unsigned cphase = 0;
+  if (tid == 0) {
+    mbar_init(&s_cbar, 1);
+    for (int i = 0; i < 16; ++i) s_prof[i] = 0;
+    s_prof[6] = clock64();
+  }
+  __syncthreads();
+  if (b == 0) {
+    // ---- diagonal blocks ----
+    for (int k = 0; k < T; ++k) {
+      const int k0 = k * NB, nb = min(NB, P.n - k0);
+      if (!wait2(P, f2_st(P) + (size_t)k * T + k, k, nullptr, 0, &s_ok, s_prof)) break;
+      TRACE(P, k, 0);
+      const long long c0 = clock64();
+      potrf128_prog_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, P.info, sm, f2_pb(P) + k, f2_pinv(P) + k, &s_sig, &s_prog);
+      __threadfence();
+      __syncthreads();
+      TRACE(P, k, 1);
+      if (tid == 0) { st_release_gpu(f2_pdone(P) + k, 1); st_release_gpu(P.flags + F2_NPAN, k + 1); s_prof[1] += clock64() - c0; s_prof[5] += 1; }
+      // the right-hand-side row n lives inside the last diagonal tile when n is not a multiple of 128
+      if (k == T - 1 && P.n_rows > P.n && P.n < T * NB) {
+        trsm64_dev(P.S, P.ld, P.n_rows, k0, nb, P.n, P.Linv + (size_t)k * NB * NB, sm, DAG_THREADS / 32);
+        __syncthreads();
+      }
+    }
+  } else if (b == 1 || b == 3) {
+    // ---- solves of tile rows k + 1 (CTA 1) and k + 2 (CTA 3) ----
+    const int d = (b == 1) ? 1 : 2;
+    for (int k = 0; k < T; ++k) {
+      if (k + d >= P.Tr) break;
+      if (!solve_row_dev(P, k + d, k, sm, &s_ok, s_prof, b == 1 ? 2 : -1)) break;
+    }
+  } else if (b == 2) {
+    // ---- last update of the diagonal tiles ----
+    for (int k = 0; k + 1 < T; ++k)
+      if (!upd_stream_dev(P, k + 1, k + 1, k, sm, &s_ok, s_prof, &s_cbar, cphase, 9)) break;
+  } else if (b == 4) {
+    // ---- last update of the first sub-diagonal tiles ----
+    for (int k = 0; k + 1 < T; ++k) {
+      if (k + 2 >= P.Tr) break;
+      if (!upd_stream_dev(P, k + 2, k + 1, k, sm, &s_ok, s_prof, &s_cbar, cphase, 10)) break;
+    }
+  } else {
+    for (;;) {
+      if (tid < 32) {
+        const int4 t = find_task2(P, b, s_prof, s_rowsv);
+        if (tid == 0) s_task = t;
+      }
+      __syncthreads();
+      const int4 t = s_task;
+      __syncthreads();
+      if (t.x == TASK2_EXIT) break;
+      const long long c0 = clock64();
+      const int k = t.w & 0xffff, nk = t.w >> 16, k0 = k * NB, nb = min(NB, P.n - k0);
+      if (t.x == TASK2_TRSM) trsm64_dev(P.S, P.ld, P.n_rows, k0, nb, t.y * 64, P.Linv + (size_t)k * NB * NB, sm, DAG_THREADS / 32);
+      else if (t.x == TASK2_UPD) upd_dev<4>(P.S, P.ld, P.n_rows, P.n, k0, NB * nk, t.y * NB, t.z * NB, sm, s_prof + 8, &s_cbar, cphase);
+      else inv_offdiag_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, sm);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        if (t.x == TASK2_TRSM) st_release_gpu(f2_sv(P) + t.y, k + 1);
+        else if (t.x == TASK2_UPD) st_release_gpu(f2_st(P) + (size_t)t.y * T + t.z, k + nk);
+        else st_release_gpu(f2_invst(P) + k, 2);
+        atomicAdd(P.flags + F2_DONE, nk);
+        const long long dt = clock64() - c0;
+        if (t.x == TASK2_TRSM) s_prof[2] += dt; else if (t.x == TASK2_UPD) s_prof[3] += dt; else s_prof[4] += dt;
+        s_prof[5] += 1;
+      }
+    }
+  }
+  if (P.prof && tid == 0) {
+    long long* o = P.prof + (size_t)b * 16;
+    for (int i = 0; i < 4; ++i) o[8 + i] = s_prof[8 + i];
+    for (int i = 0; i < 6; ++i) o[i] = s_prof[i];
+    o[6] = clock64() - s_prof[6];
+  }
+}
+
 // The one-launch substitution kernels spin on flags of CTAs with a smaller block index.  CUDA does not promise
 // in-order dispatch once a grid exceeds the resident capacity, so the grid is cut into launches of at most one
 // CTA per SM: inside a launch every CTA is resident, across launches the producers have already finished.
@@ -1787,6 +2366,9 @@ struct CholPlan {
   int n_hp = 0, n_ur = 0, n_lp = 0, grid = 0, R64 = 0, Tr = 0;
   int* dflags = nullptr;
   size_t n_dflags = 0;
+  int dag_version = 2;        // 2: scan scheduler (default), 1: ticket queues (STBA_CHOL_DAG1=1)
+  int* d_tiles = nullptr;     // DAG 2: tile list + column starts
+  int n_tiles = 0, total_units = 0, W = 2, G = 3;
   long long* prof = nullptr;
   unsigned long long* trace = nullptr;
   cudaStream_t side = nullptr, inv = nullptr;
@@ -1809,6 +2391,7 @@ static void destroy_plan(CholPlan* p) {
   if (p->ur) cudaFree(p->ur);
   if (p->hp_end) cudaFree(p->hp_end);
   if (p->dflags) cudaFree(p->dflags);
+  if (p->d_tiles) cudaFree(p->d_tiles);
   if (p->prof) cudaFree(p->prof);
   if (p->trace) cudaFree(p->trace);
   if (p->side) cudaStreamDestroy(p->side);
@@ -2051,6 +2634,101 @@ static int run_dag(CholPlan& P, cudaStream_t stream) {
   return STBA_OK;
 }
 
+
+// DAG 2 (scan scheduler): state tables, the tile list in scan order and the number of work units the workers owe.
+static int build_dag2_plan(CholPlan& P) {
+  const int n = P.n, T = (n + NB - 1) / NB, n_rows = n + 1;
+  P.Tr = (n_rows + NB - 1) / NB;
+  P.R64 = (n_rows + 63) / 64;
+  P.W = 2; P.G = 3;
+  if (const char* s = getenv("STBA_CHOL_WINDOW")) P.W = std::max(0, atoi(s));
+  if (const char* s = getenv("STBA_CHOL_AGG")) P.G = std::max(1, std::min(16, atoi(s)));
+  std::vector<int> tiles, col_start(T + 1, 0);
+  long long units = T;                               // the inverse completions
+  for (int j = 0; j < T; ++j) {
+    col_start[j] = (int)tiles.size();
+    for (int i = j; i < P.Tr; ++i) {
+      tiles.push_back(i | (j << 16));
+      const int lim = (i - j <= 1) ? j - 1 : j;      // the last panel of tiles (j, j) and (j + 1, j) belongs to CTAs 2 and 4
+      units += std::max(lim, 0);
+    }
+  }
+  col_start[T] = (int)tiles.size();
+  for (int h = 0; h < P.R64; ++h) units += std::max(0, std::min((h >> 1) - 2, T));     // panel solves of tile rows >= k + 3
+  P.n_tiles = (int)tiles.size();
+  P.total_units = (int)units;
+  std::vector<int> both(tiles);
+  both.insert(both.end(), col_start.begin(), col_start.end());
+  CKC(cudaMalloc(&P.d_tiles, both.size() * sizeof(int)));
+  CKC(cudaMemcpy(P.d_tiles, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice));
+  P.n_dflags = (size_t)F2_ARR + 4 * (size_t)T + P.Tr + P.R64 + (size_t)P.Tr * T;
+  CKC(cudaMalloc(&P.dflags, P.n_dflags * sizeof(int)));
+  int dev = 0, sms = 0;
+  CKC(cudaGetDevice(&dev));
+  CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  P.grid = sms;
+  if (const char* g = getenv("STBA_CHOL_GRID")) P.grid = std::max(6, std::min(sms, atoi(g)));
+  if (P.grid < 6) return STBA_ERR_UNSUPPORTED;
+  CKC(cudaFuncSetAttribute(k_chol_dag2, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM));
+  if (getenv("STBA_CHOL_PROF")) {
+    CKC(cudaMalloc(&P.prof, (size_t)P.grid * 16 * sizeof(long long)));
+    CKC(cudaMemset(P.prof, 0, (size_t)P.grid * 16 * sizeof(long long)));
+    CKC(cudaMalloc(&P.trace, (size_t)T * 16 * sizeof(unsigned long long)));
+    CKC(cudaMemset(P.trace, 0, (size_t)T * 16 * sizeof(unsigned long long)));
+  }
+  return STBA_OK;
+}
+
+static int run_dag2(CholPlan& P, cudaStream_t stream) {
+  const int n = P.n, ld = P.ld, T = (n + NB - 1) / NB;
+  k_put_row<<<(n + 255) / 256, 256, 0, stream>>>(P.S, ld, n, P.rhs);
+  CKC(cudaMemsetAsync(P.dflags, 0, P.n_dflags * sizeof(int), stream));
+  Dag2Params dp;
+  dp.S = P.S; dp.ld = ld; dp.n = n; dp.n_rows = n + 1; dp.T = T; dp.Tr = P.Tr; dp.R64 = P.R64;
+  dp.Linv = P.Linv; dp.info = P.info; dp.flags = P.dflags;
+  dp.total_units = P.total_units; dp.W = P.W; dp.G = P.G;
+  dp.tiles = P.d_tiles; dp.col_start = P.d_tiles + P.n_tiles; dp.n_tiles = P.n_tiles;
+  dp.prof = P.prof; dp.trace = P.trace;
+  void* args[] = {&dp};
+  CKC(cudaLaunchCooperativeKernel((const void*)k_chol_dag2, dim3(P.grid), dim3(DAG_THREADS), args, DAG_SMEM, stream));
+  k_get_row<<<(n + 255) / 256, 256, 0, stream>>>(P.S, ld, n, P.ybuf);
+  CKC(cudaMemsetAsync(P.flags, 0, (size_t)T * sizeof(int), stream));
+  for (int b0 = 0; b0 < T; b0 += substitution_chunk())
+    k_trsv_bwd_all<<<std::min(T - b0, substitution_chunk()), TBA_THREADS, TBA_SMEM, stream>>>(P.S, ld, n, T, P.Linv, P.ybuf, P.rhs, P.flags, P.info, b0);
+  CKC(cudaGetLastError());
+  P.launches = 4;
+  if (P.prof) {
+    CKC(cudaStreamSynchronize(stream));
+    std::vector<long long> h((size_t)P.grid * 16);
+    CKC(cudaMemcpy(h.data(), P.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < std::min(P.grid, 7); ++b) {
+      const long long* o = &h[(size_t)b * 16];
+      fprintf(stderr, "[chol dag2] cta %3d: wait %8lld potrf %8lld trsm %8lld upd %8lld inv %8lld tasks %5lld total %8lld | upd phases: issue %lld first %lld loop %lld store %lld\n", b, o[0], o[1], o[2], o[3],
+              o[4], o[5], o[6], o[8], o[9], o[10], o[11]);
+    }
+    long long w = 0, tr = 0, up = 0, iv = 0, nt = 0, tot = 0;
+    for (int b = 5; b < P.grid; ++b) { const long long* o = &h[(size_t)b * 16]; w += o[0]; tr += o[2]; up += o[3]; iv += o[4]; nt += o[5]; tot += o[6]; }
+    if (P.trace) {
+      std::vector<unsigned long long> tr((size_t)T * 16);
+      CKC(cudaMemcpy(tr.data(), P.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      const unsigned long long t0 = tr[0];
+      fprintf(stderr, "[chol trace] us since potrf(0) start: k | P start, P end | solve in, X ready, step0..3 start, X published, diag upd done, subdiag upd done\n");
+      fprintf(stderr, "[chol trace] potrf start times (us):");
+      for (int k = 0; k < T; ++k) fprintf(stderr, " %.0f", (double)(tr[(size_t)k * 16] - t0) * 1e-3);
+      fprintf(stderr, "\n");
+      for (int k = 0; k < T; k += (k < 4 || k + 5 > T) ? 1 : 6) {
+        fprintf(stderr, "[chol trace] %2d |", k);
+        for (int s = 0; s <= 10; ++s) fprintf(stderr, " %8.1f%s", tr[(size_t)k * 16 + s] ? (double)(tr[(size_t)k * 16 + s] - t0) * 1e-3 : -1.0, (s == 1) ? " |" : "");
+        fprintf(stderr, "\n");
+      }
+    }
+    const double nw = std::max(1, P.grid - 5);
+    fprintf(stderr, "[chol dag2] workers (mean cycles): wait %.0f trsm %.0f upd %.0f inv %.0f tasks %.1f total %.0f\n", w / nw, tr / nw, up / nw,
+            iv / nw, nt / nw, tot / nw);
+  }
+  return STBA_OK;
+}
+
 int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream, int* n_launches) {
   if (n <= 0) return STBA_OK;
   if (ld % 2 || ld < n + 1) return STBA_ERR_UNSUPPORTED;   // 16-byte cp.async rows; room for the rhs row
@@ -2067,7 +2745,8 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
     CKC(cudaMalloc(&P->flags, (size_t)T * sizeof(int)));
     CKC(cudaFuncSetAttribute(k_trsv_bwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM));
     P->dag = getenv("STBA_CHOL_GRAPH") == nullptr;
-    if (P->dag) { if (build_dag_plan(*P) != STBA_OK) return STBA_ERR_CUDA; }
+    P->dag_version = (getenv("STBA_CHOL_DAG1") || (n + 1 + NB - 1) / NB > MAX_TR) ? 1 : 2;
+    if (P->dag) { if ((P->dag_version == 2 ? build_dag2_plan(*P) : build_dag_plan(*P)) != STBA_OK) return STBA_ERR_CUDA; }
     if (!P->dag) {
     {
       // tile lists: for step k, [panel rows | column k+1 strip | the rest], stored back to back
@@ -2117,7 +2796,7 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
     }
   }
   if (P->dag) {
-    const int r = run_dag(*P, stream);
+    const int r = P->dag_version == 2 ? run_dag2(*P, stream) : run_dag(*P, stream);
     if (r != STBA_OK) return r;
     if (n_launches) *n_launches += P->launches;
     return STBA_OK;
