@@ -80,7 +80,7 @@ typedef struct stba_options {
   int32_t update_state_every_iteration;    /* 0; test_ceres.h:138 sets it for the callback */
   int32_t minimizer_progress_to_stdout;    /* 0; solver.hpp:278 */
   int32_t num_threads;                     /* accepted and ignored (reference sets 1) */
-  int32_t dense_backend;                   /* STBA_DENSE_HYBRID */
+  int32_t dense_backend;                   /* STBA_DENSE_OWN */
   double initial_trust_region_radius;      /* 1e4 */
   double max_trust_region_radius;          /* 1e16 */
   double min_trust_region_radius;          /* 1e-32 */

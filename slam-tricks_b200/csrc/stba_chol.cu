@@ -979,11 +979,17 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const double v = (c == lane) ? dl * rsl : a[c] * xd[b0 + c];
+          a[c] = v;
           if (c <= lane) D[(b0 + c) * QLD + b0 + lane] = v;
         }
         __threadfence_block();
         __syncwarp();
         if (lane == 0) *s_sig = b + 1;
+        // the finished rows go straight to global memory (one 256-byte segment per column and warp): no copy-out
+        // pass between "block column b factored" and "block column b published"
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c <= lane && b0 + lane < nb) S[(size_t)(k0 + b0 + c) * ld + k0 + b0 + lane] = a[c];
         TICK(20 + b);
       } else if (warp > b && warp < 4) {
         // (2) rows below the pivot block follow the same elimination, four columns behind at most: the former
@@ -1012,25 +1018,20 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
         while (*s_prog < base + 33) { }
         __threadfence_block();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) D[(b0 + c) * QLD + r] = a[c] * xd[b0 + c];
+        for (int c = 0; c < 32; ++c) {
+          const double v = a[c] * xd[b0 + c];
+          D[(b0 + c) * QLD + r] = v;
+          if (r < nb && b0 + c < nb) S[(size_t)(k0 + b0 + c) * ld + k0 + r] = v;
+        }
       }
       bar_workers();
       TICK(2 + 3 * b);
       TICK(3 + 3 * b);
       const int below = NB - b0 - 32;
       if (warp == 14) {
-        // block column b is final: copy it out and publish it
-        for (int c = b0; c < b0 + 32 && c < nb; ++c) {
-          double* dst = S + (size_t)(k0 + c) * ld + k0;
-          const double* srcc = D + c * QLD;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = b0 + lane + 32 * i;
-            if (r >= c && r < nb) dst[r] = srcc[r];
-          }
-        }
+        // block column b is final and on its way to global memory: the stores of the warps that own its rows
+        // happen before this point (barrier), the fence below is cumulative (the grid-sync idiom): publish it
         __threadfence();
-        __syncwarp();
         if (lane == 0) st_release_gpu(pb_flag, b + 1);
       } else if (below > 0) {
         // (3) rank-32 update of the remaining lower triangle on the FP64 tensor pipe: 16 x 16 macro tiles (four
@@ -1776,6 +1777,7 @@ struct Dag2Params {
   int* flags;               // [F2_ABORT] [F2_NPAN] [F2_DONE] . pdone[T] pb[T] pinv[T] invst[T] xpub[Tr] sv[R64] st[Tr * T]
   int total_units;
   int W, G;
+  int D;                    // tile rows k + 1 .. k + D are carried by dedicated CTAs at step k
   const int* tiles;         // every tile (i | j << 16), column by column
   const int* col_start;     // col_start[j]: position of tile (j, j) in tiles[]
   int n_tiles;
@@ -1915,29 +1917,8 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k,
     }
     if (trace_base >= 0) TRACE(P, k, trace_base + 2 + j);
     {
-      double a4[4][2];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) a4[nt][e] = Xw[(32 * j + 8 * nt + 2 * q + e) * 8 + g];
-#pragma unroll
-      for (int p = 0; p < j; ++p) {
-        const double* Lp = Lb + tu_lb_off(p) + (32 * j - 32 * p) + g;
-        const int ldp = tu_lb_ld(p);
-#pragma unroll
-        for (int kk = 0; kk < 32; kk += 4) {
-          const double a = -Xw[(32 * p + kk + q) * 8 + g];
-          const double* bs = Lp + (kk + q) * ldp;
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) dmma(a4[nt][0], a4[nt][1], a, bs[nt * 8]);
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) Xw[(32 * j + 8 * nt + 2 * q + e) * 8 + g] = a4[nt][e];
-      __syncwarp();
+      // X_j = A_j Inv_jj^T: the contributions of the earlier block columns were subtracted as soon as they were
+      // known (below), so that only this product separates "block column j published" from "X_j published"
       double out[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
       const double* Ij = Lb + tu_lb_off(j) + g;
       const int ldj = tu_lb_ld(j);
@@ -1967,6 +1948,32 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k,
         if (h2) st_release_gpu(sv + 2 * i + 1, k + 1);
         if (trace_base >= 0) TRACE(P, k, trace_base + 6);
       }
+    }
+    // right-looking inside the tile row: A_jj -= X_j L_jj,j^T for the later block columns jj (block column j of
+    // L_kk is in shared memory) — off the chain: CTA 0 is factoring block column j + 1 meanwhile
+    __syncwarp();
+#pragma unroll
+    for (int jj = j + 1; jj < 4; ++jj) {
+      double a4[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) a4[nt][e] = Xw[(32 * jj + 8 * nt + 2 * q + e) * 8 + g];
+      const double* Lp = Lb + tu_lb_off(j) + (32 * jj - 32 * j) + g;
+      const int ldp = tu_lb_ld(j);
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+        const double a = -Xw[(32 * j + kk + q) * 8 + g];
+        const double* bs = Lp + (kk + q) * ldp;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma(a4[nt][0], a4[nt][1], a, bs[nt * 8]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) Xw[(32 * jj + 8 * nt + 2 * q + e) * 8 + g] = a4[nt][e];
+      __syncwarp();
     }
   }
   if (tid == 0) { prof[2] += clock64() - c_begin; prof[5] += 1; }
@@ -2079,7 +2086,7 @@ __device__ __forceinline__ bool upd_stream_dev(const Dag2Params& P, int i, int j
   __syncthreads();
   if (tid == 0) {
     st_release_gpu(st, k + 1);
-    TRACE(P, k, trace_slot);
+    if (trace_slot >= 0) TRACE(P, k, trace_slot);
     prof[3] += clock64() - c_begin;
     prof[5] += 1;
   }
@@ -2115,8 +2122,8 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
         const bool h1 = half2_exists(P, 2 * i + 1);
         kb = h1 ? ld_relaxed(sv + 2 * i + 1) : (1 << 19);
         s_rowsv[i] = min(ka & ~ST_LOCK, kb & ~ST_LOCK);
-        const bool c0k = !(ka & ST_LOCK) && ka < np && ka + 3 <= i;
-        const bool c1k = h1 && !(kb & ST_LOCK) && kb < np && kb + 3 <= i;
+        const bool c0k = !(ka & ST_LOCK) && ka < np && ka + P.D < i;
+        const bool c1k = h1 && !(kb & ST_LOCK) && kb < np && kb + P.D < i;
         const int s0 = c0k ? ld_relaxed(st + (size_t)i * T + ka) : -1;
         const int s1 = c1k ? ld_relaxed(st + (size_t)i * T + kb) : -1;
         ok0 = c0k && s0 == ka;
@@ -2163,7 +2170,7 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = ti[u], j = tj[u];
-          if (i >= 0 && (ta[u] & ~ST_LOCK) < ((i - j <= 1) ? j - 1 : j)) jinc = min(jinc, j);
+          if (i >= 0 && (ta[u] & ~ST_LOCK) < min(j, i - P.D)) jinc = min(jinc, j);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -2172,11 +2179,14 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
           int nk = 0;
           const int i = ti[u], j = tj[u], a = ta[u];
           if (i >= 0 && !(a & ST_LOCK)) {
-            const int lim = (i - j <= 1) ? j - 1 : j;      // the last panel of tiles (j, j) and (j+1, j) belongs to CTAs 2 and 4
+            const int lim = min(j, i - P.D);      // panels k >= i - D of tile (i, j) belong to the dedicated CTAs
             const int av = min(min(s_rowsv[i], s_rowsv[j]), lim);
             nk = min(av - a, P.G);
             if (nk > 0) {
-              ok = (j <= np + P.W) || nk == P.G;
+              // the farther from the front, the longer the chunk a tile waits for: 1 panel inside the window W,
+              // one more per block column of distance, G at most — tiles catch up gradually as the front approaches
+              // instead of owing G - 1 panels when they become urgent
+              ok = av - a >= min(P.G, max(1, j - np - P.W + 1));
               fb = !ok;
             }
           }
@@ -2272,22 +2282,21 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag2(const Dag2Params P
         __syncthreads();
       }
     }
-  } else if (b == 1 || b == 3) {
-    // ---- solves of tile rows k + 1 (CTA 1) and k + 2 (CTA 3) ----
-    const int d = (b == 1) ? 1 : 2;
+  } else if (b <= P.D) {
+    // ---- solve of tile row k + b against panel k, following CTA 0 ----
     for (int k = 0; k < T; ++k) {
-      if (k + d >= P.Tr) break;
-      if (!solve_row_dev(P, k + d, k, sm, &s_ok, s_prof, b == 1 ? 2 : -1)) break;
+      if (k + b >= P.Tr) break;
+      if (!solve_row_dev(P, k + b, k, sm, &s_ok, s_prof, b == 1 ? 2 : -1)) break;
     }
-  } else if (b == 2) {
-    // ---- last update of the diagonal tiles ----
-    for (int k = 0; k + 1 < T; ++k)
-      if (!upd_stream_dev(P, k + 1, k + 1, k, sm, &s_ok, s_prof, &s_cbar, cphase, 9)) break;
-  } else if (b == 4) {
-    // ---- last update of the first sub-diagonal tiles ----
-    for (int k = 0; k + 1 < T; ++k) {
-      if (k + 2 >= P.Tr) break;
-      if (!upd_stream_dev(P, k + 2, k + 1, k, sm, &s_ok, s_prof, &s_cbar, cphase, 10)) break;
+  } else if (b <= P.D + P.D * (P.D + 1) / 2) {
+    // ---- update of tile (k + di, k + dj) with panel k, following the solves of its two tile rows ----
+    int r = b - P.D - 1, di = 1;
+    while (r >= di) { r -= di; ++di; }
+    const int dj = r + 1;
+    const int slot = (di == 1) ? 9 : (di == 2 && dj == 1) ? 10 : -1;
+    for (int k = 0; k < T; ++k) {
+      if (k + dj >= T || k + di >= P.Tr) break;
+      if (!upd_stream_dev(P, k + di, k + dj, k, sm, &s_ok, s_prof, &s_cbar, cphase, slot)) break;
     }
   } else {
     for (;;) {
@@ -2367,8 +2376,9 @@ struct CholPlan {
   int* dflags = nullptr;
   size_t n_dflags = 0;
   int dag_version = 2;        // 2: scan scheduler (default), 1: ticket queues (STBA_CHOL_DAG1=1)
+  cudaStream_t pool_stream = nullptr;   // DAG 2: every buffer is stream-ordered (pooled): no cudaMalloc / cudaFree stalls per problem
   int* d_tiles = nullptr;     // DAG 2: tile list + column starts
-  int n_tiles = 0, total_units = 0, W = 2, G = 3;
+  int n_tiles = 0, total_units = 0, W = 2, G = 8, D = 3;
   long long* prof = nullptr;
   unsigned long long* trace = nullptr;
   cudaStream_t side = nullptr, inv = nullptr;
@@ -2381,6 +2391,18 @@ struct CholPlan {
 
 static void destroy_plan(CholPlan* p) {
   if (!p) return;
+  if (p->pool_stream) {      // DAG 2: stream-ordered buffers
+    cudaStream_t st = p->pool_stream;
+    if (p->Linv) cudaFreeAsync(p->Linv, st);
+    if (p->ybuf) cudaFreeAsync(p->ybuf, st);
+    if (p->flags) cudaFreeAsync(p->flags, st);
+    if (p->dflags) cudaFreeAsync(p->dflags, st);
+    if (p->d_tiles) cudaFreeAsync(p->d_tiles, st);
+    if (p->prof) cudaFree(p->prof);
+    if (p->trace) cudaFree(p->trace);
+    delete p;
+    return;
+  }
   if (p->exec) cudaGraphExecDestroy(p->exec);
   if (p->Linv) cudaFree(p->Linv);
   if (p->ybuf) cudaFree(p->ybuf);
@@ -2636,11 +2658,12 @@ static int run_dag(CholPlan& P, cudaStream_t stream) {
 
 
 // DAG 2 (scan scheduler): state tables, the tile list in scan order and the number of work units the workers owe.
-static int build_dag2_plan(CholPlan& P) {
+static int build_dag2_plan(CholPlan& P, cudaStream_t stream) {
   const int n = P.n, T = (n + NB - 1) / NB, n_rows = n + 1;
   P.Tr = (n_rows + NB - 1) / NB;
   P.R64 = (n_rows + 63) / 64;
-  P.W = 2; P.G = 3;
+  P.W = 2; P.G = 8; P.D = 3;
+  if (const char* s = getenv("STBA_CHOL_DEPTH")) P.D = std::max(1, std::min(4, atoi(s)));
   if (const char* s = getenv("STBA_CHOL_WINDOW")) P.W = std::max(0, atoi(s));
   if (const char* s = getenv("STBA_CHOL_AGG")) P.G = std::max(1, std::min(16, atoi(s)));
   std::vector<int> tiles, col_start(T + 1, 0);
@@ -2649,27 +2672,33 @@ static int build_dag2_plan(CholPlan& P) {
     col_start[j] = (int)tiles.size();
     for (int i = j; i < P.Tr; ++i) {
       tiles.push_back(i | (j << 16));
-      const int lim = (i - j <= 1) ? j - 1 : j;      // the last panel of tiles (j, j) and (j + 1, j) belongs to CTAs 2 and 4
-      units += std::max(lim, 0);
+      units += std::max(std::min(j, i - P.D), 0);      // panels k >= i - D of tile (i, j) belong to the dedicated CTAs
     }
   }
   col_start[T] = (int)tiles.size();
-  for (int h = 0; h < P.R64; ++h) units += std::max(0, std::min((h >> 1) - 2, T));     // panel solves of tile rows >= k + 3
+  for (int h = 0; h < P.R64; ++h) units += std::max(0, std::min((h >> 1) - P.D, T));     // panel solves of tile rows > k + D
   P.n_tiles = (int)tiles.size();
   P.total_units = (int)units;
   std::vector<int> both(tiles);
   both.insert(both.end(), col_start.begin(), col_start.end());
-  CKC(cudaMalloc(&P.d_tiles, both.size() * sizeof(int)));
-  CKC(cudaMemcpy(P.d_tiles, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CKC(cudaMallocAsync((void**)&P.d_tiles, both.size() * sizeof(int), stream));
+  CKC(cudaMemcpyAsync(P.d_tiles, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, stream));    // pageable source: staged before the call returns
   P.n_dflags = (size_t)F2_ARR + 4 * (size_t)T + P.Tr + P.R64 + (size_t)P.Tr * T;
-  CKC(cudaMalloc(&P.dflags, P.n_dflags * sizeof(int)));
-  int dev = 0, sms = 0;
-  CKC(cudaGetDevice(&dev));
-  CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CKC(cudaMallocAsync((void**)&P.dflags, P.n_dflags * sizeof(int), stream));
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CKC(cudaGetDevice(&dev));
+    CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   P.grid = sms;
-  if (const char* g = getenv("STBA_CHOL_GRID")) P.grid = std::max(6, std::min(sms, atoi(g)));
-  if (P.grid < 6) return STBA_ERR_UNSUPPORTED;
-  CKC(cudaFuncSetAttribute(k_chol_dag2, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM));
+  const int n_ded = 1 + P.D + P.D * (P.D + 1) / 2;
+  if (const char* g = getenv("STBA_CHOL_GRID")) P.grid = std::max(n_ded + 1, std::min(sms, atoi(g)));
+  if (P.grid < n_ded + 1) return STBA_ERR_UNSUPPORTED;
+  {
+    static bool attr_set = false;      // per process (one device per process)
+    if (!attr_set) { CKC(cudaFuncSetAttribute(k_chol_dag2, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM)); attr_set = true; }
+  }
   if (getenv("STBA_CHOL_PROF")) {
     CKC(cudaMalloc(&P.prof, (size_t)P.grid * 16 * sizeof(long long)));
     CKC(cudaMemset(P.prof, 0, (size_t)P.grid * 16 * sizeof(long long)));
@@ -2686,7 +2715,7 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
   Dag2Params dp;
   dp.S = P.S; dp.ld = ld; dp.n = n; dp.n_rows = n + 1; dp.T = T; dp.Tr = P.Tr; dp.R64 = P.R64;
   dp.Linv = P.Linv; dp.info = P.info; dp.flags = P.dflags;
-  dp.total_units = P.total_units; dp.W = P.W; dp.G = P.G;
+  dp.total_units = P.total_units; dp.W = P.W; dp.G = P.G; dp.D = P.D;
   dp.tiles = P.d_tiles; dp.col_start = P.d_tiles + P.n_tiles; dp.n_tiles = P.n_tiles;
   dp.prof = P.prof; dp.trace = P.trace;
   void* args[] = {&dp};
@@ -2701,13 +2730,14 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
     CKC(cudaStreamSynchronize(stream));
     std::vector<long long> h((size_t)P.grid * 16);
     CKC(cudaMemcpy(h.data(), P.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    for (int b = 0; b < std::min(P.grid, 7); ++b) {
+    const int n_ded = 1 + P.D + P.D * (P.D + 1) / 2;
+    for (int b = 0; b < std::min(P.grid, n_ded + 2); ++b) {
       const long long* o = &h[(size_t)b * 16];
       fprintf(stderr, "[chol dag2] cta %3d: wait %8lld potrf %8lld trsm %8lld upd %8lld inv %8lld tasks %5lld total %8lld | upd phases: issue %lld first %lld loop %lld store %lld\n", b, o[0], o[1], o[2], o[3],
               o[4], o[5], o[6], o[8], o[9], o[10], o[11]);
     }
     long long w = 0, tr = 0, up = 0, iv = 0, nt = 0, tot = 0;
-    for (int b = 5; b < P.grid; ++b) { const long long* o = &h[(size_t)b * 16]; w += o[0]; tr += o[2]; up += o[3]; iv += o[4]; nt += o[5]; tot += o[6]; }
+    for (int b = n_ded; b < P.grid; ++b) { const long long* o = &h[(size_t)b * 16]; w += o[0]; tr += o[2]; up += o[3]; iv += o[4]; nt += o[5]; tot += o[6]; }
     if (P.trace) {
       std::vector<unsigned long long> tr((size_t)T * 16);
       CKC(cudaMemcpy(tr.data(), P.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -2722,7 +2752,17 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
         fprintf(stderr, "\n");
       }
     }
-    const double nw = std::max(1, P.grid - 5);
+#ifdef STBA_CHOL_TIMING
+    {
+      long long hc[64];
+      cudaMemcpyFromSymbol(hc, g_potrf_clk, sizeof(hc));
+      fprintf(stderr, "[potrf128 clocks, last panel]");
+      for (int i = 1; i <= 16; ++i) fprintf(stderr, " %d:%lld", i, hc[i] - hc[i - 1]);
+      for (int b = 0; b < 4; ++b) fprintf(stderr, " potf2_%d:%lld", b, hc[20 + b] - hc[b ? 1 + 3 * b : 1]);
+      fprintf(stderr, "\n");
+    }
+#endif
+    const double nw = std::max(1, P.grid - n_ded);
     fprintf(stderr, "[chol dag2] workers (mean cycles): wait %.0f trsm %.0f upd %.0f inv %.0f tasks %.1f total %.0f\n", w / nw, tr / nw, up / nw,
             iv / nw, nt / nw, tot / nw);
   }
@@ -2739,14 +2779,25 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
     P->S = S; P->n = n; P->ld = ld; P->rhs = rhs; P->info = dev_info;
     const int T = (n + NB - 1) / NB;
     P->rest64 = getenv("STBA_SYRK_TM") ? atoi(getenv("STBA_SYRK_TM")) == 64 : false;
-    CKC(cudaMalloc(&P->Linv, (size_t)T * NB * NB * sizeof(double)));
-    CKC(cudaMemset(P->Linv, 0, (size_t)T * NB * NB * sizeof(double)));   // upper triangles stay zero forever
-    CKC(cudaMalloc(&P->ybuf, (size_t)T * NB * sizeof(double)));
-    CKC(cudaMalloc(&P->flags, (size_t)T * sizeof(int)));
-    CKC(cudaFuncSetAttribute(k_trsv_bwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM));
     P->dag = getenv("STBA_CHOL_GRAPH") == nullptr;
     P->dag_version = (getenv("STBA_CHOL_DAG1") || (n + 1 + NB - 1) / NB > MAX_TR) ? 1 : 2;
-    if (P->dag) { if ((P->dag_version == 2 ? build_dag2_plan(*P) : build_dag_plan(*P)) != STBA_OK) return STBA_ERR_CUDA; }
+    if (P->dag && P->dag_version == 2) {
+      P->pool_stream = stream;
+      CKC(cudaMallocAsync((void**)&P->Linv, (size_t)T * NB * NB * sizeof(double), stream));
+      CKC(cudaMemsetAsync(P->Linv, 0, (size_t)T * NB * NB * sizeof(double), stream));   // upper triangles stay zero forever
+      CKC(cudaMallocAsync((void**)&P->ybuf, (size_t)T * NB * sizeof(double), stream));
+      CKC(cudaMallocAsync((void**)&P->flags, (size_t)T * sizeof(int), stream));
+    } else {
+      CKC(cudaMalloc(&P->Linv, (size_t)T * NB * NB * sizeof(double)));
+      CKC(cudaMemset(P->Linv, 0, (size_t)T * NB * NB * sizeof(double)));   // upper triangles stay zero forever
+      CKC(cudaMalloc(&P->ybuf, (size_t)T * NB * sizeof(double)));
+      CKC(cudaMalloc(&P->flags, (size_t)T * sizeof(int)));
+    }
+    {
+      static bool attr_set = false;
+      if (!attr_set) { CKC(cudaFuncSetAttribute(k_trsv_bwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM)); attr_set = true; }
+    }
+    if (P->dag) { if ((P->dag_version == 2 ? build_dag2_plan(*P, stream) : build_dag_plan(*P)) != STBA_OK) return STBA_ERR_CUDA; }
     if (!P->dag) {
     {
       // tile lists: for step k, [panel rows | column k+1 strip | the rest], stored back to back

@@ -856,7 +856,7 @@ void stba_options_init(stba_options* o) {
   o->update_state_every_iteration = 0;
   o->minimizer_progress_to_stdout = 0;
   o->num_threads = 1;
-  o->dense_backend = STBA_DENSE_HYBRID;    // fastest measured (profiles/r1_dense_notes.md); STBA_DENSE_OWN is all hand-written
+  o->dense_backend = STBA_DENSE_OWN;       // all hand-written and the fastest measured (profiles/r2_dense_notes.md); the library back ends stay as yard-sticks
   o->initial_trust_region_radius = 1e4;
   o->max_trust_region_radius = 1e16;
   o->min_trust_region_radius = 1e-32;
@@ -1208,6 +1208,7 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
     if (info) CK(cudaMemcpy(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost));
   }
   tw.reset();
+  ws.reset();      // stream-ordered buffers: released while the stream exists
   cudaStreamSynchronize(st);
   if (h) cusolverDnDestroy(h);
   cudaFree(dS); cudaFree(dS0); cudaFree(dr); cudaFree(dr0); cudaFree(dinfo); if (work) cudaFree(work);

@@ -144,7 +144,7 @@ class BAEngine:
                    "stba_ba_reduced_system")
         return S.T.copy(), rhs     # column-major on the device -> row-major view
 
-    def solve_step(self, dense_backend=capi.DENSE_HYBRID):
+    def solve_step(self, dense_backend=capi.DENSE_OWN):
         yc = np.empty((self.n_cam, 6)); yl = np.empty((self.n_lm, 3)); mcc = C.c_double(0)
         capi.check(self._L.stba_ba_solve_step(self._h, dense_backend, capi.dptr(yc), capi.dptr(yl), C.byref(mcc)),
                    "stba_ba_solve_step")

@@ -278,6 +278,77 @@ __global__ void k_potf2(const double* A, double* out, long long* cyc, int* info,
   if (threadIdx.x == 0) cyc[0] = t1 - t0;
   for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) out[e] = D[(e / 32) * QLD + e % 32];
 }
+
+// V6: V4 exactly as it sits in potrf128_prog_dev: progress counter for the follower warps (volatile shared
+// store after a block-level fence every four columns), pivot check by ballot, scale through shared memory
+__device__ __forceinline__ void v6(double* D, double* xd, double* cb, int* info, int lane, volatile int* s_prog, bool fences) {
+  double a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? D[c * QLD + lane] : 0.0;
+  cb[lane] = a[0];
+  if (fences) __threadfence_block();
+  __syncwarp();
+  if (lane == 0) *s_prog = 1;
+  double tp = 0.0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double* col = cb + j * 32;
+    const double d = col[j];
+    const double nx = (j + 1 < 32) ? col[j + 1] : 0.0;
+    if (j > 0) {
+      const double* pc = cb + (j - 1) * 32;
+#pragma unroll
+      for (int k = j + 2; k < 32; ++k) a[k] = fma(-tp, pc[k], a[k]);
+    }
+    const double u = a[j] * nx;
+    const double r = fast_rcp(d);
+    if (j + 1 < 32) {
+      a[j + 1] = fma(-u, r, a[j + 1]);
+      cb[(j + 1) * 32 + lane] = a[j + 1];
+      if (fences && ((j & 3) == 3 || j == 30)) __threadfence_block();
+      __syncwarp();
+      if (((j & 3) == 3 || j == 30) && lane == 0) *s_prog = j + 2;
+    }
+    tp = a[j] * r;
+    if (j + 2 < 32) a[j + 2] = fma(-tp, col[j + 2], a[j + 2]);
+  }
+  const double dl = cb[lane * 32 + lane];
+  const unsigned badm = __ballot_sync(0xffffffffu, !(dl > 0.0));
+  if (badm && lane == 0) atomicCAS(info, 0, __ffs(badm));
+  const double rsl = fast_rsqrt(dl);
+  xd[lane] = rsl;
+  if (fences) __threadfence_block();
+  __syncwarp();
+  if (lane == 0) *s_prog = 33;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const double v = (c == lane) ? dl * rsl : a[c] * xd[c];
+    if (c <= lane) D[c * QLD + lane] = v;
+  }
+}
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) k_potf2_big(const double* A, double* out, long long* cyc, int* info) {
+  __shared__ double D[32 * QLD];
+  __shared__ double xd[32];
+  __shared__ __align__(16) double cb[32 * 32];
+  __shared__ int s_prog;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) D[(e / 32) * QLD + e % 32] = A[e];
+  if (threadIdx.x == 0) s_prog = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  if (warp == 0) {
+    v6(D, xd, cb, info, lane, &s_prog, MODE != 0);
+  } else if (MODE == 2 && warp < 4) {
+    // three warps polling the progress counter like the followers do
+    volatile int* sp = &s_prog;
+    while (*sp < 33) { }
+  }
+  long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) cyc[0] = t1 - t0;
+  for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) out[e] = D[(e / 32) * QLD + e % 32];
+}
 int main() {
   std::vector<double> A(1024), L(1024), R(1024);
   srand(1);
@@ -316,6 +387,20 @@ int main() {
     for (int j = 0; j < 32; ++j)
       for (int i = j; i < 32; ++i) err = fmax(err, fabs(L[j * 32 + i] - R[j * 32 + i]));
     printf("variant %d: %lld cycles (%.0f per pivot), max |L - ref| = %.2e  %s\n", v, h, h / 32.0, err, cudaGetErrorString(cudaGetLastError()));
+  }
+  for (int v = 0; v < 3; ++v) {
+    long long h = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      if (v == 0) k_potf2_big<0><<<1, 512>>>(dA, dO, cyc, info);
+      if (v == 1) k_potf2_big<1><<<1, 512>>>(dA, dO, cyc, info);
+      if (v == 2) k_potf2_big<2><<<1, 512>>>(dA, dO, cyc, info);
+      cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    }
+    cudaMemcpy(L.data(), dO, 8192, cudaMemcpyDeviceToHost);
+    double err = 0;
+    for (int j = 0; j < 32; ++j)
+      for (int i = j; i < 32; ++i) err = fmax(err, fabs(L[j * 32 + i] - R[j * 32 + i]));
+    printf("512-thread kernel, mode %d (0 no fences, 1 fences, 2 fences + 3 polling warps): %lld cycles, max err %.2e %s\n", v, h, err, cudaGetErrorString(cudaGetLastError()));
   }
   return 0;
 }
