@@ -853,7 +853,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 //     inverts the 32 x 32 diagonal factor blocks as they appear and publishes them (pinv): the consumers of
 //     the panel (the solve of the next tile row) start on block column b while b + 1 is being factored.
 constexpr int QLD = NB + 4;      // (q QLD + g) mod 16 distinct over a half-warp: conflict-free DMMA fragments
-constexpr int PROG_SMEM = (NB * QLD + NB + 32 * 32) * (int)sizeof(double);
+constexpr int PROG_SMEM = (NB * QLD + NB + 32 * 32 + 32 * QLD) * (int)sizeof(double);
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 480;" ::: "memory"); }
 
@@ -869,10 +869,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
 
 __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv,
                                                   int* __restrict__ info, double* sm, int* pb_flag, int* pinv_flag,
-                                                  volatile int* s_sig, volatile int* s_prog) {
+                                                  volatile int* s_sig, volatile int* s_prog,
+                                                  const int* xflag = nullptr, int xbase = 0, int n_rows = 0, const int* abort_flag = nullptr) {
   double* D = sm;                  // D[c * QLD + r], lower triangle
   double* xd = sm + NB * QLD;      // 1 / L_jj
   double* cb = xd + NB;            // 32 x 32: column j of the pivot block as it was when it became the pivot column
+  double* Xb = cb + 32 * 32;       // 32 x QLD: one block column of the previous panel's rows of this tile (streamed update)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   TICK(0);
@@ -898,6 +900,78 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
   }
   if (tid == 0) { *s_sig = 0; *s_prog = 0; }
   __syncthreads();
+  if (xflag) {
+    // ---- the LAST update of this tile, A_kk -= X X^T with X = L(k, k-1), applied here while the solve of tile row k
+    //      against panel k-1 is still publishing its block columns (xflag >= xbase + b + 1): the tile never makes the
+    //      round trip  update CTA -> global memory -> flag -> this CTA  between the last solve step and the first pivot
+    for (int b = 0; b < 4; ++b) {
+      if (tid == 0) {
+        long long spins = 0;
+        while (ld_relaxed(xflag) < xbase + b + 1) {
+          if ((++spins & 255) == 0 && abort_flag && ld_relaxed(abort_flag)) break;
+          if (spins > (1ll << 21)) break;
+        }
+        ld_acquire_gpu(xflag);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + i * 512;
+        const int c = e >> 6, r2 = (e & 63) * 2;
+        const double* src = S + (size_t)(k0 - NB + 32 * b + c) * ld + k0 + r2;
+        double2 v = make_double2(0.0, 0.0);
+        if (r2 + 1 < nb) v = __ldcg(reinterpret_cast<const double2*>(src));
+        else if (r2 < nb) v.x = __ldcg(src);
+        Xb[c * QLD + r2] = v.x;
+        Xb[c * QLD + r2 + 1] = v.y;
+      }
+      __syncthreads();
+      {
+        int cnt = 0;
+        for (int ti = 0; ti < 8; ++ti)
+          for (int tj = 0; tj <= ti; ++tj, ++cnt) {
+            if ((cnt & 15) != warp) continue;
+            const int r0 = 16 * ti, c0 = 16 * tj;
+            double acc[2][2][2];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) acc[mi][ni][e] = D[(c0 + 8 * ni + 2 * q + e) * QLD + r0 + 8 * mi + g];
+#pragma unroll
+            for (int kk = 0; kk < 32; kk += 4) {
+              const double* colp = Xb + (kk + q) * QLD;
+              const double a0 = -colp[r0 + g], a1 = -colp[r0 + 8 + g];
+              const double bb0 = colp[c0 + g], bb1 = colp[c0 + 8 + g];
+              dmma(acc[0][0][0], acc[0][0][1], a0, bb0);
+              dmma(acc[0][1][0], acc[0][1][1], a0, bb1);
+              dmma(acc[1][0][0], acc[1][0][1], a1, bb0);
+              dmma(acc[1][1][0], acc[1][1][1], a1, bb1);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 2; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) D[(c0 + 8 * ni + 2 * q + e) * QLD + r0 + 8 * mi + g] = acc[mi][ni][e];
+          }
+      }
+      __syncthreads();
+    }
+    // the right-hand-side row (row n of S) lives inside the last diagonal tile when n is not a multiple of 128: its
+    // share of this update, one thread per column
+    if (n_rows > k0 + nb && nb < NB && tid < nb) {
+      const int rr = k0 + nb;          // = n
+      double acc = 0.0;
+      for (int kk = 0; kk < NB; ++kk) {
+        const double* colp = S + (size_t)(k0 - NB + kk) * ld;
+        acc = fma(__ldcg(colp + rr), __ldcg(colp + k0 + tid), acc);
+      }
+      S[(size_t)(k0 + tid) * ld + rr] -= acc;
+    }
+    __syncthreads();
+  }
   TICK(1);
   if (warp == 15) {
     // ---- inverse of the 32 x 32 diagonal factor blocks, as they are produced ----
@@ -2268,10 +2342,12 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag2(const Dag2Params P
     // ---- diagonal blocks ----
     for (int k = 0; k < T; ++k) {
       const int k0 = k * NB, nb = min(NB, P.n - k0);
-      if (!wait2(P, f2_st(P) + (size_t)k * T + k, k, nullptr, 0, &s_ok, s_prof)) break;
+      // every update but the last (panel k - 1: streamed in by potrf128_prog_dev from the solve of tile row k)
+      if (!wait2(P, f2_st(P) + (size_t)k * T + k, k - 1, nullptr, 0, &s_ok, s_prof)) break;
       TRACE(P, k, 0);
       const long long c0 = clock64();
-      potrf128_prog_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, P.info, sm, f2_pb(P) + k, f2_pinv(P) + k, &s_sig, &s_prog);
+      potrf128_prog_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, P.info, sm, f2_pb(P) + k, f2_pinv(P) + k, &s_sig, &s_prog,
+                        k > 0 ? f2_xpub(P) + k : nullptr, 4 * (k - 1), P.n_rows, P.flags + F2_ABORT);
       __threadfence();
       __syncthreads();
       TRACE(P, k, 1);
@@ -2288,12 +2364,13 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag2(const Dag2Params P
       if (k + b >= P.Tr) break;
       if (!solve_row_dev(P, k + b, k, sm, &s_ok, s_prof, b == 1 ? 2 : -1)) break;
     }
-  } else if (b <= P.D + P.D * (P.D + 1) / 2) {
-    // ---- update of tile (k + di, k + dj) with panel k, following the solves of its two tile rows ----
-    int r = b - P.D - 1, di = 1;
+  } else if (b <= P.D + P.D * (P.D + 1) / 2 - 1) {
+    // ---- update of tile (k + di, k + dj) with panel k, following the solves of its two tile rows; (1, 1), the last
+    //      update of the diagonal tile, happens inside CTA 0 ----
+    int r = b - P.D, di = 1;
     while (r >= di) { r -= di; ++di; }
     const int dj = r + 1;
-    const int slot = (di == 1) ? 9 : (di == 2 && dj == 1) ? 10 : -1;
+    const int slot = (di == 2 && dj == 1) ? 10 : (di == 2 && dj == 2) ? 9 : -1;
     for (int k = 0; k < T; ++k) {
       if (k + dj >= T || k + di >= P.Tr) break;
       if (!upd_stream_dev(P, k + di, k + dj, k, sm, &s_ok, s_prof, &s_cbar, cphase, slot)) break;
@@ -2378,7 +2455,7 @@ struct CholPlan {
   int dag_version = 2;        // 2: scan scheduler (default), 1: ticket queues (STBA_CHOL_DAG1=1)
   cudaStream_t pool_stream = nullptr;   // DAG 2: every buffer is stream-ordered (pooled): no cudaMalloc / cudaFree stalls per problem
   int* d_tiles = nullptr;     // DAG 2: tile list + column starts
-  int n_tiles = 0, total_units = 0, W = 2, G = 8, D = 3;
+  int n_tiles = 0, total_units = 0, W = 2, G = 8, D = 2;
   long long* prof = nullptr;
   unsigned long long* trace = nullptr;
   cudaStream_t side = nullptr, inv = nullptr;
@@ -2662,7 +2739,7 @@ static int build_dag2_plan(CholPlan& P, cudaStream_t stream) {
   const int n = P.n, T = (n + NB - 1) / NB, n_rows = n + 1;
   P.Tr = (n_rows + NB - 1) / NB;
   P.R64 = (n_rows + 63) / 64;
-  P.W = 2; P.G = 8; P.D = 3;
+  P.W = 2; P.G = 8; P.D = 2;
   if (const char* s = getenv("STBA_CHOL_DEPTH")) P.D = std::max(1, std::min(4, atoi(s)));
   if (const char* s = getenv("STBA_CHOL_WINDOW")) P.W = std::max(0, atoi(s));
   if (const char* s = getenv("STBA_CHOL_AGG")) P.G = std::max(1, std::min(16, atoi(s)));
@@ -2692,7 +2769,7 @@ static int build_dag2_plan(CholPlan& P, cudaStream_t stream) {
     CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   P.grid = sms;
-  const int n_ded = 1 + P.D + P.D * (P.D + 1) / 2;
+  const int n_ded = P.D + P.D * (P.D + 1) / 2;
   if (const char* g = getenv("STBA_CHOL_GRID")) P.grid = std::max(n_ded + 1, std::min(sms, atoi(g)));
   if (P.grid < n_ded + 1) return STBA_ERR_UNSUPPORTED;
   {
@@ -2730,7 +2807,7 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
     CKC(cudaStreamSynchronize(stream));
     std::vector<long long> h((size_t)P.grid * 16);
     CKC(cudaMemcpy(h.data(), P.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    const int n_ded = 1 + P.D + P.D * (P.D + 1) / 2;
+    const int n_ded = P.D + P.D * (P.D + 1) / 2;
     for (int b = 0; b < std::min(P.grid, n_ded + 2); ++b) {
       const long long* o = &h[(size_t)b * 16];
       fprintf(stderr, "[chol dag2] cta %3d: wait %8lld potrf %8lld trsm %8lld upd %8lld inv %8lld tasks %5lld total %8lld | upd phases: issue %lld first %lld loop %lld store %lld\n", b, o[0], o[1], o[2], o[3],
