@@ -870,7 +870,8 @@ __device__ __forceinline__ double fast_rcp(double d) {
 __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld, int k0, int nb, double* __restrict__ Linv,
                                                   int* __restrict__ info, double* sm, int* pb_flag, int* pinv_flag,
                                                   volatile int* s_sig, volatile int* s_prog,
-                                                  const int* xflag = nullptr, int xbase = 0, int n_rows = 0, const int* abort_flag = nullptr) {
+                                                  const int* xflag = nullptr, int xbase = 0, int n_rows = 0, const int* abort_flag = nullptr,
+                                                  const int* xflag2 = nullptr) {
   double* D = sm;                  // D[c * QLD + r], lower triangle
   double* xd = sm + NB * QLD;      // 1 / L_jj
   double* cb = xd + NB;            // 32 x 32: column j of the pivot block as it was when it became the pivot column
@@ -907,11 +908,12 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
     for (int b = 0; b < 4; ++b) {
       if (tid == 0) {
         long long spins = 0;
-        while (ld_relaxed(xflag) < xbase + b + 1) {
+        while (ld_relaxed(xflag) < xbase + b + 1 || (xflag2 && ld_relaxed(xflag2) < xbase + b + 1)) {
           if ((++spins & 255) == 0 && abort_flag && ld_relaxed(abort_flag)) break;
           if (spins > (1ll << 21)) break;
         }
         ld_acquire_gpu(xflag);
+        if (xflag2) ld_acquire_gpu(xflag2);
       }
       __syncthreads();
 #pragma unroll
@@ -1848,7 +1850,7 @@ struct Dag2Params {
   int ld, n, n_rows, T, Tr, R64;
   double* Linv;
   int* info;
-  int* flags;               // [F2_ABORT] [F2_NPAN] [F2_DONE] . pdone[T] pb[T] pinv[T] invst[T] xpub[Tr] sv[R64] st[Tr * T]
+  int* flags;               // [F2_ABORT] [F2_NPAN] [F2_DONE] [F2_JMIN] . pdone[T] pb[T] pinv[T] invst[T] xpub[2 Tr] sv[R64] st[Tr * T] hd[Tr * T]
   int total_units;
   int W, G;
   int D;                    // tile rows k + 1 .. k + D are carried by dedicated CTAs at step k
@@ -1863,8 +1865,9 @@ __device__ __forceinline__ int* f2_pb(const Dag2Params& P) { return f2_pdone(P) 
 __device__ __forceinline__ int* f2_pinv(const Dag2Params& P) { return f2_pb(P) + P.T; }
 __device__ __forceinline__ int* f2_invst(const Dag2Params& P) { return f2_pinv(P) + P.T; }
 __device__ __forceinline__ int* f2_xpub(const Dag2Params& P) { return f2_invst(P) + P.T; }
-__device__ __forceinline__ int* f2_sv(const Dag2Params& P) { return f2_xpub(P) + P.Tr; }
+__device__ __forceinline__ int* f2_sv(const Dag2Params& P) { return f2_xpub(P) + 2 * P.Tr; }
 __device__ __forceinline__ int* f2_st(const Dag2Params& P) { return f2_sv(P) + P.R64; }
+__device__ __forceinline__ int* f2_hd(const Dag2Params& P) { return f2_st(P) + (size_t)P.Tr * P.T; }
 __device__ __forceinline__ bool half2_exists(const Dag2Params& P, int h) { return h * 64 < P.n_rows; }
 
 __device__ __forceinline__ void dag2_abort(const Dag2Params& P) {
@@ -1921,16 +1924,41 @@ __device__ __forceinline__ int wait2v(const Dag2Params& P, const int* f0, const 
   return ok;
 }
 
+// CTA-wide wait until *f0 >= v, *f1 >= v and *f2 >= v (null pointers are skipped).  Returns false after an abort.
+__device__ __forceinline__ bool wait3(const Dag2Params& P, const int* f0, const int* f1, const int* f2, int v, int* s_ok, long long* t_wait) {
+  if (threadIdx.x == 0) {
+    const long long c0 = clock64();
+    long long spins = 0;
+    int ok = 1;
+    for (;;) {
+      if ((!f0 || ld_relaxed(f0) >= v) && (!f1 || ld_relaxed(f1) >= v) && (!f2 || ld_relaxed(f2) >= v)) {
+        if (f0) ld_acquire_gpu(f0);
+        if (f1) ld_acquire_gpu(f1);
+        if (f2) ld_acquire_gpu(f2);
+        break;
+      }
+      if ((++spins & 255) == 0 && ld_relaxed(P.flags + F2_ABORT)) { ok = 0; break; }
+      if (spins > SPIN_LIMIT) { dag2_abort(P); ok = 0; break; }
+    }
+    *s_ok = ok;
+    *t_wait += clock64() - c0;
+  }
+  __syncthreads();
+  const int ok = *s_ok;
+  __syncthreads();
+  return ok != 0;
+}
+
 // ---- solve of one tile row against panel k, following CTA 0 block column by block column ----------------
 // X = A(i, k) L_kk^-T by forward substitution over the four 32-column blocks as they are published (pb / pinv),
 // each warp carrying 8 of the 128 rows (warp-private strips: no CTA-wide synchronisation inside a step).  Every
 // finished block column is published (xpub[i] = 4 k + b + 1) for the update CTAs; at the end the two halves of
 // the tile row are marked solved for block column k.
-__device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k, double* sm, int* s_ok, long long* prof, int trace_base) {
+__device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int half, int k, double* sm, int* s_ok, long long* prof, int trace_base) {
   const int T = P.T, ld = P.ld, n_rows = P.n_rows;
   double* __restrict__ S = P.S;
-  const int r0 = i * NB, k0 = k * NB, nb = min(NB, P.n - k0);
-  const bool h2 = half2_exists(P, 2 * i + 1);
+  if (!half2_exists(P, 2 * i + half)) return true;
+  const int r0 = i * NB + 64 * half, k0 = k * NB, nb = min(NB, P.n - k0);
   const double* Linv = P.Linv + (size_t)k * NB * NB;
   double* Xs = sm;                        // Xs[(strip * NB + col) * 8 + row_in_strip]
   double* Lb = sm + 16 * NB * 8;
@@ -1942,22 +1970,20 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k,
   if (trace_base >= 0) TRACE(P, k, trace_base + 1);
   const long long c_begin = clock64();
   for (int c = warp; c < NB; c += 16) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int r2 = 2 * lane + 64 * s, row = r0 + r2;
-      double* dst = Xs + ((r2 >> 3) * NB + c) * 8 + (r2 & 7);
-      const double* src = S + (size_t)(k0 + c) * ld + row;
-      if (c < nb && row + 1 < n_rows) {
-        cp_async16(dst, src, true);
-      } else {
-        dst[0] = (c < nb && row < n_rows) ? __ldcg(src) : 0.0;
-        dst[1] = 0.0;
-      }
+    const int r2 = 2 * lane, row = r0 + r2;
+    double* dst = Xs + ((r2 >> 3) * NB + c) * 8 + (r2 & 7);
+    const double* src = S + (size_t)(k0 + c) * ld + row;
+    if (c < nb && row + 1 < n_rows) {
+      cp_async16(dst, src, true);
+    } else {
+      dst[0] = (c < nb && row < n_rows) ? __ldcg(src) : 0.0;
+      dst[1] = 0.0;
     }
   }
   cp_async_commit();
-  double* Xw = Xs + warp * NB * 8;
-  const int row = r0 + warp * 8 + g;
+  const bool cw = warp < 8;             // 64 rows = 8 strips: warps 8..15 only help with the loads and the barriers
+  double* Xw = Xs + (warp & 7) * NB * 8;
+  const int row = r0 + (warp & 7) * 8 + g;
   int loaded = 0;                  // block columns of L_kk already requested
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -1990,7 +2016,7 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k,
       __syncthreads();
     }
     if (trace_base >= 0) TRACE(P, k, trace_base + 2 + j);
-    {
+    if (cw) {
       // X_j = A_j Inv_jj^T: the contributions of the earlier block columns were subtracted as soon as they were
       // known (below), so that only this product separates "block column j published" from "X_j published"
       double out[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
@@ -2016,10 +2042,9 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k,
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-      st_release_gpu(f2_xpub(P) + i, 4 * k + j + 1);
-      if (j == 3) {      // the tile row is solved for block column k
-        st_release_gpu(sv + 2 * i, k + 1);
-        if (h2) st_release_gpu(sv + 2 * i + 1, k + 1);
+      st_release_gpu(f2_xpub(P) + 2 * i + half, 4 * k + j + 1);
+      if (j == 3) {      // these 64 rows are solved for block column k
+        st_release_gpu(sv + 2 * i + half, k + 1);
         if (trace_base >= 0) TRACE(P, k, trace_base + 6);
       }
     }
@@ -2027,7 +2052,7 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k,
     // L_kk is in shared memory) — off the chain: CTA 0 is factoring block column j + 1 meanwhile
     __syncwarp();
 #pragma unroll
-    for (int jj = j + 1; jj < 4; ++jj) {
+    for (int jj = j + 1; cw && jj < 4; ++jj) {
       double a4[4][2];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
@@ -2059,57 +2084,51 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int k,
 // accumulators hold the C tile while the four rank-32 updates arrive (xpub).  16 warps, 4 x 4, warp tile 32 x 32;
 // on a diagonal tile only the warp tiles on or below the diagonal work (same map as upd_dev).
 constexpr int US_LD = NB + 4;
-constexpr int US_SMEM = cmax(2 * 32 * US_LD, NB * LDC) * (int)sizeof(double);
-__device__ __forceinline__ bool upd_stream_dev(const Dag2Params& P, int i, int j, int k, double* smem, int* s_ok, long long* prof,
+constexpr int LDC64 = 64 + 2;
+__device__ __forceinline__ bool upd_stream_dev(const Dag2Params& P, int i, int j, int half, int k, double* smem, int* s_ok, long long* prof,
                                                unsigned long long* cbar, unsigned& cphase, int trace_slot) {
+  // 64 rows of the tile (half), 128 columns: 16 warps as 4 (rows of 16) x 4 (columns of 32)
+  if (!half2_exists(P, 2 * i + half)) return true;
   const int T = P.T, lda = P.ld, n_rows = P.n_rows, n_cols = P.n;
   double* __restrict__ S = P.S;
-  const int i0 = i * NB, j0 = j * NB, k0 = k * NB;
+  const int i0 = i * NB + 64 * half, j0 = j * NB, k0 = k * NB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const bool diag = i == j;
-  int wm = warp >> 2, wn = warp & 3;
-  bool active = true;
-  if (diag) {
-    active = warp < 10;
-    switch (warp) {
-      case 0: wm = 0; wn = 0; break;  case 1: wm = 1; wn = 0; break;  case 2: wm = 1; wn = 1; break;  case 3: wm = 2; wn = 0; break;
-      case 4: wm = 2; wn = 1; break;  case 5: wm = 2; wn = 2; break;  case 6: wm = 3; wn = 0; break;  case 7: wm = 3; wn = 1; break;
-      case 8: wm = 3; wn = 2; break;  case 9: wm = 3; wn = 3; break;  default: wm = 0; wn = 0; break;
-    }
-  }
-  // the tile has received every update the workers owe it (panels 0 .. k-1)
+  const int wm = warp >> 2, wn = warp & 3;
+  // diagonal tile: warp tiles entirely above the diagonal carry no arithmetic
+  const bool active = !(diag && 32 * wn > 64 * half + 16 * wm + 15);
   int* st = f2_st(P) + (size_t)i * T + j;
   if (!wait2(P, st, k, nullptr, 0, s_ok, prof)) return false;
   const long long c_begin = clock64();
-  double acc[4][4][2];
+  double acc[2][4][2];
   {
     const int ncol = min(NB, n_cols - j0);
-    const unsigned col_bytes = (unsigned)min(NB, lda - i0) * 8u;
+    const unsigned col_bytes = (unsigned)min(64, lda - i0) * 8u;
     if (tid == 0) mbar_expect_tx(cbar, col_bytes * (unsigned)ncol);
     __syncthreads();
     if (tid < ncol) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      bulk_g2s(smem + tid * LDC, S + (size_t)(j0 + tid) * lda + i0, col_bytes, cbar);
+      bulk_g2s(smem + tid * LDC64, S + (size_t)(j0 + tid) * lda + i0, col_bytes, cbar);
     }
     mbar_wait(cbar, cphase & 1);
     ++cphase;
     if (active) {
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-          for (int e = 0; e < 2; ++e) acc[mt][nt][e] = smem[(wn * 32 + nt * 8 + 2 * q + e) * LDC + wm * 32 + mt * 8 + g];
+          for (int e = 0; e < 2; ++e) acc[mt][nt][e] = smem[(wn * 32 + nt * 8 + 2 * q + e) * LDC64 + wm * 16 + mt * 8 + g];
     }
     __syncthreads();
   }
-  double* As = smem;                     // [32][US_LD]
-  double* Bs = smem + 32 * US_LD;
-  const int* xi = f2_xpub(P) + i;
-  const int* xj = f2_xpub(P) + j;
+  double* As = smem;                     // [32][US_LD]: 64 rows of tile row i
+  double* Bs = smem + 32 * US_LD;        // [32][US_LD]: 128 rows of tile row j
+  const int* xa = f2_xpub(P) + 2 * i + half;
+  const int* xb0 = f2_xpub(P) + 2 * j;
+  const int* xb1 = half2_exists(P, 2 * j + 1) ? f2_xpub(P) + 2 * j + 1 : nullptr;
   for (int b = 0; b < 4; ++b) {
-    if (!wait2(P, xi, 4 * k + b + 1, diag ? nullptr : xj, 4 * k + b + 1, s_ok, prof)) return false;
-    // 32 columns x 128 rows of both operands
+    if (!wait3(P, xa, xb0, xb1, 4 * k + b + 1, s_ok, prof)) return false;
 #pragma unroll
     for (int p = 0; p < 32 * 64 / DAG_THREADS; ++p) {
       const int piece = tid + p * DAG_THREADS;
@@ -2118,24 +2137,24 @@ __device__ __forceinline__ bool upd_stream_dev(const Dag2Params& P, int i, int j
       const bool kin = k0 + kc < n_cols;
       const int ra = i0 + r2, rb = j0 + r2;
       const double* colp = S + (size_t)(kin ? k0 + kc : k0) * lda;
-      cp_async16(As + kk * US_LD + r2, colp + (ra < n_rows ? ra : 0), kin && ra < n_rows);
-      if (!diag) cp_async16(Bs + kk * US_LD + r2, colp + (rb < n_rows ? rb : 0), kin && rb < n_rows);
+      if (r2 < 64) cp_async16(As + kk * US_LD + r2, colp + (ra < n_rows ? ra : 0), kin && ra < n_rows);
+      cp_async16(Bs + kk * US_LD + r2, colp + (rb < n_rows ? rb : 0), kin && rb < n_rows);
     }
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
     if (active) {
-      const double* as = As + wm * 32 + g;
-      const double* bs = (diag ? As : Bs) + wn * 32 + g;
+      const double* as = As + wm * 16 + g;
+      const double* bs = Bs + wn * 32 + g;
 #pragma unroll
       for (int kk = 0; kk < 32; kk += 4) {
-        double a[4], bb[4];
+        double a[2], bb[4];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) a[mt] = -as[(kk + q) * US_LD + mt * 8];
+        for (int mt = 0; mt < 2; ++mt) a[mt] = -as[(kk + q) * US_LD + mt * 8];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) bb[nt] = bs[(kk + q) * US_LD + nt * 8];
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], bb[nt]);
       }
@@ -2144,8 +2163,8 @@ __device__ __forceinline__ bool upd_stream_dev(const Dag2Params& P, int i, int j
   }
   if (active) {
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-      const int r = i0 + wm * 32 + mt * 8 + g;
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = i0 + wm * 16 + mt * 8 + g;
       if (r >= n_rows) continue;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
@@ -2159,8 +2178,14 @@ __device__ __forceinline__ bool upd_stream_dev(const Dag2Params& P, int i, int j
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    st_release_gpu(st, k + 1);
-    if (trace_slot >= 0) TRACE(P, k, trace_slot);
+    // the second half to arrive publishes the tile (its fence orders the first half's stores, observed through the counter)
+    const int need = half2_exists(P, 2 * i + 1) ? 2 : 1;
+    const int old = atomicAdd(f2_hd(P) + (size_t)i * T + j, 1);
+    if ((old + 1) % need == 0) {
+      __threadfence();
+      st_release_gpu(st, k + 1);
+      if (trace_slot >= 0) TRACE(P, k, trace_slot);
+    }
     prof[3] += clock64() - c_begin;
     prof[5] += 1;
   }
@@ -2347,7 +2372,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag2(const Dag2Params P
       TRACE(P, k, 0);
       const long long c0 = clock64();
       potrf128_prog_dev(P.S, P.ld, k0, nb, P.Linv + (size_t)k * NB * NB, P.info, sm, f2_pb(P) + k, f2_pinv(P) + k, &s_sig, &s_prog,
-                        k > 0 ? f2_xpub(P) + k : nullptr, 4 * (k - 1), P.n_rows, P.flags + F2_ABORT);
+                        k > 0 ? f2_xpub(P) + 2 * k : nullptr, 4 * (k - 1), P.n_rows, P.flags + F2_ABORT,
+                        (k > 0 && half2_exists(P, 2 * k + 1)) ? f2_xpub(P) + 2 * k + 1 : nullptr);
       __threadfence();
       __syncthreads();
       TRACE(P, k, 1);
@@ -2358,22 +2384,24 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag2(const Dag2Params P
         __syncthreads();
       }
     }
-  } else if (b <= P.D) {
-    // ---- solve of tile row k + b against panel k, following CTA 0 ----
+  } else if (b <= 2 * P.D) {
+    // ---- solve of 64 rows of tile row k + di against panel k, following CTA 0 ----
+    const int di = (b - 1) / 2 + 1, half = (b - 1) & 1;
     for (int k = 0; k < T; ++k) {
-      if (k + b >= P.Tr) break;
-      if (!solve_row_dev(P, k + b, k, sm, &s_ok, s_prof, b == 1 ? 2 : -1)) break;
+      if (k + di >= P.Tr) break;
+      if (!solve_row_dev(P, k + di, half, k, sm, &s_ok, s_prof, b == 1 ? 2 : -1)) break;
     }
-  } else if (b <= P.D + P.D * (P.D + 1) / 2 - 1) {
-    // ---- update of tile (k + di, k + dj) with panel k, following the solves of its two tile rows; (1, 1), the last
-    //      update of the diagonal tile, happens inside CTA 0 ----
-    int r = b - P.D, di = 1;
+  } else if (b <= 2 * P.D + P.D * (P.D + 1) - 2) {
+    // ---- update of 64 rows of tile (k + di, k + dj) with panel k, following the solves of its two tile rows; (1, 1),
+    //      the last update of the diagonal tile, happens inside CTA 0 ----
+    const int u = b - 2 * P.D - 1, half = u & 1;
+    int r = u / 2 + 1, di = 1;
     while (r >= di) { r -= di; ++di; }
     const int dj = r + 1;
-    const int slot = (di == 2 && dj == 1) ? 10 : (di == 2 && dj == 2) ? 9 : -1;
+    const int slot = half ? -1 : (di == 2 && dj == 1) ? 10 : (di == 2 && dj == 2) ? 9 : -1;
     for (int k = 0; k < T; ++k) {
       if (k + dj >= T || k + di >= P.Tr) break;
-      if (!upd_stream_dev(P, k + di, k + dj, k, sm, &s_ok, s_prof, &s_cbar, cphase, slot)) break;
+      if (!upd_stream_dev(P, k + di, k + dj, half, k, sm, &s_ok, s_prof, &s_cbar, cphase, slot)) break;
     }
   } else {
     for (;;) {
@@ -2455,7 +2483,7 @@ struct CholPlan {
   int dag_version = 2;        // 2: scan scheduler (default), 1: ticket queues (STBA_CHOL_DAG1=1)
   cudaStream_t pool_stream = nullptr;   // DAG 2: every buffer is stream-ordered (pooled): no cudaMalloc / cudaFree stalls per problem
   int* d_tiles = nullptr;     // DAG 2: tile list + column starts
-  int n_tiles = 0, total_units = 0, W = 2, G = 8, D = 2;
+  int n_tiles = 0, total_units = 0, W = 2, G = 8, D = 1;
   long long* prof = nullptr;
   unsigned long long* trace = nullptr;
   cudaStream_t side = nullptr, inv = nullptr;
@@ -2739,7 +2767,7 @@ static int build_dag2_plan(CholPlan& P, cudaStream_t stream) {
   const int n = P.n, T = (n + NB - 1) / NB, n_rows = n + 1;
   P.Tr = (n_rows + NB - 1) / NB;
   P.R64 = (n_rows + 63) / 64;
-  P.W = 2; P.G = 8; P.D = 2;
+  P.W = 2; P.G = 8; P.D = 1;
   if (const char* s = getenv("STBA_CHOL_DEPTH")) P.D = std::max(1, std::min(4, atoi(s)));
   if (const char* s = getenv("STBA_CHOL_WINDOW")) P.W = std::max(0, atoi(s));
   if (const char* s = getenv("STBA_CHOL_AGG")) P.G = std::max(1, std::min(16, atoi(s)));
@@ -2760,7 +2788,7 @@ static int build_dag2_plan(CholPlan& P, cudaStream_t stream) {
   both.insert(both.end(), col_start.begin(), col_start.end());
   CKC(cudaMallocAsync((void**)&P.d_tiles, both.size() * sizeof(int), stream));
   CKC(cudaMemcpyAsync(P.d_tiles, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, stream));    // pageable source: staged before the call returns
-  P.n_dflags = (size_t)F2_ARR + 4 * (size_t)T + P.Tr + P.R64 + (size_t)P.Tr * T;
+  P.n_dflags = (size_t)F2_ARR + 4 * (size_t)T + 2 * P.Tr + P.R64 + 2 * (size_t)P.Tr * T;
   CKC(cudaMallocAsync((void**)&P.dflags, P.n_dflags * sizeof(int), stream));
   static int sms = 0;
   if (!sms) {
@@ -2769,7 +2797,7 @@ static int build_dag2_plan(CholPlan& P, cudaStream_t stream) {
     CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   P.grid = sms;
-  const int n_ded = P.D + P.D * (P.D + 1) / 2;
+  const int n_ded = 2 * P.D + P.D * (P.D + 1) - 1;
   if (const char* g = getenv("STBA_CHOL_GRID")) P.grid = std::max(n_ded + 1, std::min(sms, atoi(g)));
   if (P.grid < n_ded + 1) return STBA_ERR_UNSUPPORTED;
   {
@@ -2807,7 +2835,7 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
     CKC(cudaStreamSynchronize(stream));
     std::vector<long long> h((size_t)P.grid * 16);
     CKC(cudaMemcpy(h.data(), P.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    const int n_ded = P.D + P.D * (P.D + 1) / 2;
+    const int n_ded = 2 * P.D + P.D * (P.D + 1) - 1;
     for (int b = 0; b < std::min(P.grid, n_ded + 2); ++b) {
       const long long* o = &h[(size_t)b * 16];
       fprintf(stderr, "[chol dag2] cta %3d: wait %8lld potrf %8lld trsm %8lld upd %8lld inv %8lld tasks %5lld total %8lld | upd phases: issue %lld first %lld loop %lld store %lld\n", b, o[0], o[1], o[2], o[3],
