@@ -424,6 +424,28 @@ def run_ba(args):
                                          "note": "stba_visibility: predicate + ordered compaction, host buffers in and out; the time is dominated by the device-to-host copy of the lists (28 B per visible pair into pageable memory); the kernels take 3.8 ms in total (ncu: profiles/r1_launches_front.md)"},
                           "triangulate": {"landmarks": n_lm_total, "observations": n_obs_total, "kernel_ms": tri_ms, "e2e_ms": 1e3 * (t3 - t2),
                                           "mean_lm_iterations": float(its.mean())}}
+        # the same three stages chained through DEVICE memory (the C entry points take host or device pointers):
+        # visibility -> triangulation -> stba_ba_create -> solve, nothing but counts and the summary crosses PCIe
+        dq = torch.as_tensor(d["cam_q"], device="cuda"); dt = torch.as_tensor(d["cam_t"], device="cuda"); dp = torch.as_tensor(d["lm"], device="cuda")
+        doc = torch.as_tensor(d["obs_cam"], device="cuda"); dol = torch.as_tensor(d["obs_lm"], device="cuda"); duv = torch.as_tensor(d["obs_uv"], device="cuda")
+        stba.front.visibility_device(dq, dt, dp)                       # warm-up (stream-ordered pool, attributes)
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        vis_d = stba.front.visibility_device(dq, dt, dp)
+        torch.cuda.synchronize()
+        t5 = time.perf_counter()
+        lm_d, _, _, _, tri_ms_d = stba.front.triangulate_device(dq, dt, dp, doc, dol, duv)
+        torch.cuda.synchronize()
+        t6 = time.perf_counter()
+        e_d = stba.engine.BAEngine.from_device(dq, dt, lm_d, doc, dol, duv, cam_const=d["cam_const"])
+        torch.cuda.synchronize()
+        t7 = time.perf_counter()
+        e_d.close()
+        extra["front"]["device_hand_off"] = {"visibility_ms": 1e3 * (t5 - t4), "visible": int(vis_d["obs_cam"].shape[0]), "triangulate_ms": 1e3 * (t6 - t5),
+                                              "triangulate_kernel_ms": tri_ms_d, "ba_create_ms": 1e3 * (t7 - t6),
+                                              "note": "torch CUDA tensors in and out of stba_visibility / stba_triangulate / stba_ba_create (cudaMemcpyDefault inside): "
+                                                      "the 590 MB of lists never leave HBM; visibility runs its counting pass twice (count, then fill)"}
+        del vis_d, lm_d
     if rank == 0:
         extra["phase_ms_per_solve"] = {k: v for k, v in last.phase_ms.items()}
         extra["iterations_per_solve"] = n_iters(last)

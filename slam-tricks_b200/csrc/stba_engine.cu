@@ -329,9 +329,9 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CK(cudaMemsetAsync(yc, 0, 6 * (size_t)std::max(ncam, 1) * sizeof(double), stream));
 
   tr.mark("cudaMalloc");
-  CK(cudaMemcpyAsync(obs_cam, h_oc, nobs * sizeof(int), cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(obs_lm, h_ol, nobs * sizeof(int), cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(obs_uv, h_uv, 2 * nobs * sizeof(double), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(obs_cam, h_oc, nobs * sizeof(int), cudaMemcpyDefault, stream));
+  CK(cudaMemcpyAsync(obs_lm, h_ol, nobs * sizeof(int), cudaMemcpyDefault, stream));
+  CK(cudaMemcpyAsync(obs_uv, h_uv, 2 * nobs * sizeof(double), cudaMemcpyDefault, stream));
   CK(cudaMemcpyAsync(cam_const, h_const.data(), ncam, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(free_of, h_free.data(), ncam * sizeof(int), cudaMemcpyHostToDevice, stream));
   if (has_lm_const) CK(cudaMemcpyAsync(lm_const, h_lc, nlm, cudaMemcpyHostToDevice, stream));
@@ -440,12 +440,12 @@ int Engine::build_pairs() {
 int Engine::set_state(const double* h_q, const double* h_t, const double* h_lm) {
   CK(cudaSetDevice(device));
   if (n_cam) {
-    CK(cudaMemcpyAsync(cam_q, h_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(cam_t, h_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(cam_q, h_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyDefault, stream));
+    CK(cudaMemcpyAsync(cam_t, h_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyDefault, stream));
   }
   if (n_lm) {
     // stage the packed [n,3] array in lm4_2 and pad on the device
-    CK(cudaMemcpyAsync(lm4_2, h_lm, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(lm4_2, h_lm, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyDefault, stream));
     LAUNCH(this, k_pad_lm, (n_lm + 255) / 256, 256, n_lm, lm4_2, lm4);
   }
   CK(cudaStreamSynchronize(stream));
@@ -456,11 +456,11 @@ int Engine::set_state(const double* h_q, const double* h_t, const double* h_lm) 
 
 int Engine::get_state(double* h_q, double* h_t, double* h_lm) {
   CK(cudaSetDevice(device));
-  if (n_cam && h_q) CK(cudaMemcpyAsync(h_q, cam_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyDeviceToHost, stream));
-  if (n_cam && h_t) CK(cudaMemcpyAsync(h_t, cam_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (n_cam && h_q) CK(cudaMemcpyAsync(h_q, cam_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyDefault, stream));
+  if (n_cam && h_t) CK(cudaMemcpyAsync(h_t, cam_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyDefault, stream));
   if (n_lm && h_lm) {
     LAUNCH(this, k_unpad_lm, (n_lm + 255) / 256, 256, n_lm, lm4, lm4_2);
-    CK(cudaMemcpyAsync(h_lm, lm4_2, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_lm, lm4_2, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyDefault, stream));
   }
   CK(cudaStreamSynchronize(stream));
   return STBA_OK;

@@ -375,6 +375,12 @@ k_triangulate(int n_lm, const double* __restrict__ W, const int64_t* __restrict_
   term[l] = tt;
 }
 
+// range check of a device-resident obs_cam (host arrays are checked on the host)
+__global__ void k_cam_range(int64_t n, const int* __restrict__ oc, int n_cam, int* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (oc[i] < 0 || oc[i] >= n_cam)) *bad = 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -398,14 +404,15 @@ int stba_visibility(int device, int32_t n_cam, int32_t n_lm, const double* cam_q
   CK(b.get(&d_q, 4 * (size_t)n_cam)); CK(b.get(&d_t, 3 * (size_t)n_cam)); CK(b.get(&d_p, 3 * (size_t)n_lm));
   CK(b.get(&d_W, (size_t)kW * n_cam)); CK(b.get(&d_cur, (size_t)n_lm)); CK(b.get(&d_cdeg, (size_t)n_cam));
   CK(b.get(&d_lptr, (size_t)n_lm + 1)); CK(b.get(&d_cptr, (size_t)n_cam + 1));
-  CK(cudaMemcpyAsync(d_q, cam_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyHostToDevice, b.s));
-  CK(cudaMemcpyAsync(d_t, cam_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyHostToDevice, b.s));
-  CK(cudaMemcpyAsync(d_p, pts, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyHostToDevice, b.s));
+  CK(cudaMemcpyAsync(d_q, cam_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyDefault, b.s));
+  CK(cudaMemcpyAsync(d_t, cam_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyDefault, b.s));
+  CK(cudaMemcpyAsync(d_p, pts, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyDefault, b.s));
   CK(cudaMemsetAsync(d_cur, 0, (size_t)n_lm * sizeof(int), b.s));
   CK(cudaMemsetAsync(d_cdeg, 0, (size_t)n_cam * sizeof(int), b.s));
   k_world_to_camera<<<(n_cam + 127) / 128, 128, 0, b.s>>>(n_cam, d_q, d_t, d_W, 1);
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
+  static int sm_count_of[64] = {0};       // cudaGetDeviceProperties costs milliseconds: one attribute query per device and process
+  if (device < 64 && !sm_count_of[device]) CK(cudaDeviceGetAttribute(&sm_count_of[device], cudaDevAttrMultiProcessorCount, device));
+  struct { int multiProcessorCount; } prop = {device < 64 ? sm_count_of[device] : 148};
   const int smem = kVisCamChunk * kW * (int)sizeof(double) + kVisCamChunk * (int)sizeof(int);
   CK(cudaFuncSetAttribute(k_vis_lm<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(k_vis_lm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -417,8 +424,8 @@ int stba_visibility(int device, int32_t n_cam, int32_t n_lm, const double* cam_q
   k_scan_i32_i64<<<1, 1024, 0, b.s>>>(n_cam, d_cdeg, d_cptr);
   int64_t total = 0;
   CK(cudaMemcpyAsync(&total, d_lptr + n_lm, sizeof(int64_t), cudaMemcpyDeviceToHost, b.s));
-  if (lm_deg) CK(cudaMemcpyAsync(lm_deg, d_cur, (size_t)n_lm * sizeof(int), cudaMemcpyDeviceToHost, b.s));
-  if (cam_deg) CK(cudaMemcpyAsync(cam_deg, d_cdeg, (size_t)n_cam * sizeof(int), cudaMemcpyDeviceToHost, b.s));
+  if (lm_deg) CK(cudaMemcpyAsync(lm_deg, d_cur, (size_t)n_lm * sizeof(int), cudaMemcpyDefault, b.s));
+  if (cam_deg) CK(cudaMemcpyAsync(cam_deg, d_cdeg, (size_t)n_cam * sizeof(int), cudaMemcpyDefault, b.s));
   CK(cudaStreamSynchronize(b.s));
   *n_obs = total;
   const bool want_lists = obs_cam || obs_lm || obs_uv || cam_lm;
@@ -431,10 +438,10 @@ int stba_visibility(int device, int32_t n_cam, int32_t n_lm, const double* cam_q
                                                 d_uv);
   if (cam_lm) k_vis_cam<<<(n_cam + wpb - 1) / wpb, kVisThreads, 0, b.s>>>(n_cam, n_lm, d_W, d_p, half_w, half_h, d_cptr, d_cl);
   CK(cudaGetLastError());
-  if (obs_cam) CK(cudaMemcpyAsync(obs_cam, d_oc, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, b.s));
-  if (obs_lm) CK(cudaMemcpyAsync(obs_lm, d_ol, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, b.s));
-  if (obs_uv) CK(cudaMemcpyAsync(obs_uv, d_uv, 2 * (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, b.s));
-  if (cam_lm) CK(cudaMemcpyAsync(cam_lm, d_cl, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, b.s));
+  if (obs_cam) CK(cudaMemcpyAsync(obs_cam, d_oc, (size_t)total * sizeof(int), cudaMemcpyDefault, b.s));
+  if (obs_lm) CK(cudaMemcpyAsync(obs_lm, d_ol, (size_t)total * sizeof(int), cudaMemcpyDefault, b.s));
+  if (obs_uv) CK(cudaMemcpyAsync(obs_uv, d_uv, 2 * (size_t)total * sizeof(double), cudaMemcpyDefault, b.s));
+  if (cam_lm) CK(cudaMemcpyAsync(cam_lm, d_cl, (size_t)total * sizeof(int), cudaMemcpyDefault, b.s));
   CK(cudaStreamSynchronize(b.s));
   return STBA_OK;
 }
@@ -444,8 +451,17 @@ int stba_triangulate(int device, int32_t n_cam, int32_t n_lm, int64_t n_obs, con
                      int32_t* iterations, double* final_cost, int32_t* termination, float* kernel_ms) {
   if (n_cam < 0 || n_lm < 0 || n_obs < 0 || (n_lm && !lm) || (n_obs && (!obs_cam || !obs_lm || !obs_uv || !cam_q || !cam_t)))
     return STBA_ERR_INVALID_ARGUMENT;
-  for (int64_t i = 0; i < n_obs; ++i)
-    if (obs_cam[i] < 0 || obs_cam[i] >= n_cam) return STBA_ERR_INVALID_ARGUMENT;
+  // Array arguments may live in host or in device memory (unified addressing: the copies below are
+  // cudaMemcpyDefault).  Host arrays are range-checked here, device arrays by k_cam_range on the device.
+  bool oc_on_device = false;
+  if (n_obs) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, obs_cam) == cudaSuccess) oc_on_device = pa.type == cudaMemoryTypeDevice;
+    else cudaGetLastError();
+  }
+  if (!oc_on_device)
+    for (int64_t i = 0; i < n_obs; ++i)
+      if (obs_cam[i] < 0 || obs_cam[i] >= n_cam) return STBA_ERR_INVALID_ARGUMENT;
   DevBuf b;
   const int st = open_device(device, b);
   if (st != STBA_OK) return st;
@@ -460,18 +476,19 @@ int stba_triangulate(int device, int32_t n_cam, int32_t n_lm, int64_t n_obs, con
   CK(b.get(&d_oc, (size_t)n_obs)); CK(b.get(&d_ol, (size_t)n_obs)); CK(b.get(&d_deg, (size_t)n_lm)); CK(b.get(&d_bad, 1));
   CK(b.get(&d_it, (size_t)n_lm)); CK(b.get(&d_term, (size_t)n_lm)); CK(b.get(&d_ptr, (size_t)n_lm + 1));
   if (n_cam) {
-    CK(cudaMemcpyAsync(d_q, cam_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyHostToDevice, b.s));
-    CK(cudaMemcpyAsync(d_t, cam_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyHostToDevice, b.s));
+    CK(cudaMemcpyAsync(d_q, cam_q, 4 * (size_t)n_cam * sizeof(double), cudaMemcpyDefault, b.s));
+    CK(cudaMemcpyAsync(d_t, cam_t, 3 * (size_t)n_cam * sizeof(double), cudaMemcpyDefault, b.s));
   }
-  CK(cudaMemcpyAsync(d_lm, lm, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyHostToDevice, b.s));
+  CK(cudaMemcpyAsync(d_lm, lm, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyDefault, b.s));
   if (n_obs) {
-    CK(cudaMemcpyAsync(d_oc, obs_cam, (size_t)n_obs * sizeof(int), cudaMemcpyHostToDevice, b.s));
-    CK(cudaMemcpyAsync(d_ol, obs_lm, (size_t)n_obs * sizeof(int), cudaMemcpyHostToDevice, b.s));
-    CK(cudaMemcpyAsync(d_uv, obs_uv, 2 * (size_t)n_obs * sizeof(double), cudaMemcpyHostToDevice, b.s));
+    CK(cudaMemcpyAsync(d_oc, obs_cam, (size_t)n_obs * sizeof(int), cudaMemcpyDefault, b.s));
+    CK(cudaMemcpyAsync(d_ol, obs_lm, (size_t)n_obs * sizeof(int), cudaMemcpyDefault, b.s));
+    CK(cudaMemcpyAsync(d_uv, obs_uv, 2 * (size_t)n_obs * sizeof(double), cudaMemcpyDefault, b.s));
   }
   CK(cudaMemsetAsync(d_deg, 0, (size_t)n_lm * sizeof(int), b.s));
   CK(cudaMemsetAsync(d_bad, 0, sizeof(int), b.s));
   if (n_cam) k_world_to_camera<<<(n_cam + 127) / 128, 128, 0, b.s>>>(n_cam, d_q, d_t, d_W, 0);
+  if (n_obs && oc_on_device) k_cam_range<<<(unsigned)((n_obs + 255) / 256), 256, 0, b.s>>>(n_obs, d_oc, n_cam, d_bad);
   if (n_obs) k_lm_hist<<<(unsigned)((n_obs + 255) / 256), 256, 0, b.s>>>(n_obs, d_ol, n_lm, d_deg, d_bad);
   k_scan_i32_i64<<<1, 1024, 0, b.s>>>(n_lm, d_deg, d_ptr);
   int bad = 0;
@@ -489,10 +506,10 @@ int stba_triangulate(int device, int32_t n_cam, int32_t n_lm, int64_t n_obs, con
   k_triangulate<<<(n_lm + 127) / 128, 128, 0, b.s>>>(n_lm, d_W, d_ptr, d_oc, d_uv, d_lm, t, d_it, d_cost, d_term);
   CK(cudaEventRecord(e1, b.s));
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(lm, d_lm, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyDeviceToHost, b.s));
-  if (iterations) CK(cudaMemcpyAsync(iterations, d_it, (size_t)n_lm * sizeof(int), cudaMemcpyDeviceToHost, b.s));
-  if (final_cost) CK(cudaMemcpyAsync(final_cost, d_cost, (size_t)n_lm * sizeof(double), cudaMemcpyDeviceToHost, b.s));
-  if (termination) CK(cudaMemcpyAsync(termination, d_term, (size_t)n_lm * sizeof(int), cudaMemcpyDeviceToHost, b.s));
+  CK(cudaMemcpyAsync(lm, d_lm, 3 * (size_t)n_lm * sizeof(double), cudaMemcpyDefault, b.s));
+  if (iterations) CK(cudaMemcpyAsync(iterations, d_it, (size_t)n_lm * sizeof(int), cudaMemcpyDefault, b.s));
+  if (final_cost) CK(cudaMemcpyAsync(final_cost, d_cost, (size_t)n_lm * sizeof(double), cudaMemcpyDefault, b.s));
+  if (termination) CK(cudaMemcpyAsync(termination, d_term, (size_t)n_lm * sizeof(int), cudaMemcpyDefault, b.s));
   CK(cudaStreamSynchronize(b.s));
   if (kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -73,6 +73,37 @@ class BAEngine:
                                        capi.CREATE_LINEARIZE_ONLY if linearize_only else 0), "stba_ba_create_ex")
         self._L = L
 
+    @classmethod
+    def from_device(cls, cam_q, cam_t, lm, obs_cam, obs_lm, obs_uv, cam_const=None, lm_const=None):
+        """Device hand-off: the arrays are torch CUDA tensors (e.g. straight from `front.visibility_device` /
+        `front.triangulate_device`); `stba_ba_create` copies them device-to-device.  cam_const / lm_const stay small
+        host arrays (the free-camera map is built on the host)."""
+        L = capi.lib()
+        self = cls.__new__(cls)
+        dev = cam_q.device
+        self.n_cam, self.n_lm, self.n_obs = cam_q.shape[0], lm.shape[0], obs_cam.shape[0]
+        cc = np.ascontiguousarray(cam_const if cam_const is not None else np.zeros(self.n_cam), dtype=np.uint8)
+        lc = np.ascontiguousarray(lm_const, dtype=np.uint8) if lm_const is not None else None
+        self.cam_const = cc.astype(bool)
+        tp = lambda t, ct: C.cast(C.c_void_p(t.contiguous().data_ptr()), C.POINTER(ct))
+        keep = [cam_q.contiguous(), cam_t.contiguous(), lm.contiguous(), obs_cam.contiguous(), obs_lm.contiguous(), obs_uv.contiguous()]
+        self._h = C.c_void_p()
+        capi.check(L.stba_ba_create_ex(C.byref(self._h), dev.index or 0, self.n_cam, self.n_lm, self.n_obs, tp(keep[0], C.c_double),
+                                       tp(keep[1], C.c_double), tp(keep[2], C.c_double), tp(keep[3], C.c_int32), tp(keep[4], C.c_int32),
+                                       tp(keep[5], C.c_double), capi.bptr(cc), capi.bptr(lc), 0), "stba_ba_create_ex")
+        self._L = L
+        return self
+
+    def get_state_device(self):
+        """State as torch CUDA tensors (device-to-device copy): (cam_q [n,4], cam_t [n,3], lm [n,3])."""
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        q = torch.empty((self.n_cam, 4), dtype=torch.float64, device=dev); t = torch.empty((self.n_cam, 3), dtype=torch.float64, device=dev)
+        p = torch.empty((self.n_lm, 3), dtype=torch.float64, device=dev)
+        tp = lambda x: C.cast(C.c_void_p(x.data_ptr()), C.POINTER(C.c_double))
+        capi.check(self._L.stba_ba_get_state(self._h, tp(q), tp(t), tp(p)), "stba_ba_get_state")
+        return q, t, p
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._L.stba_ba_destroy(self._h)

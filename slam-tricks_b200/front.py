@@ -44,6 +44,49 @@ def triangulate(cam_q, cam_t, lm0, obs_cam, obs_lm, obs_uv, options=None, device
     return lm, its, cost, [capi.TERMINATION[int(x)] for x in term], float(ms.value)
 
 
+def _tptr(t, ctype):
+    return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(ctype))
+
+
+def visibility_device(cam_q, cam_t, pts, half_w=HALF_W, half_h=HALF_H, round_uv_f32=True):
+    """Device hand-off form of `visibility`: torch CUDA tensors in, torch CUDA tensors out (the C entry point takes
+    host or device pointers alike).  Nothing but the 8-byte observation count crosses PCIe; the lists feed
+    `triangulate_device` and `engine.BAEngine` directly."""
+    import torch
+    L = capi.lib()
+    dev = cam_q.device
+    n_cam, n_lm = cam_q.shape[0], pts.shape[0]
+    q = cam_q.contiguous(); t = cam_t.contiguous(); p = pts.contiguous()
+    n = C.c_int64(0)
+    lm_deg = torch.empty(n_lm, dtype=torch.int32, device=dev); cam_deg = torch.empty(n_cam, dtype=torch.int32, device=dev)
+    args = (dev.index or 0, n_cam, n_lm, _tptr(q, C.c_double), _tptr(t, C.c_double), _tptr(p, C.c_double), half_w, half_h, int(round_uv_f32))
+    capi.check(L.stba_visibility(*args, 0, C.byref(n), None, None, None, None, None, None), "stba_visibility")
+    m = int(n.value)
+    oc = torch.empty(m, dtype=torch.int32, device=dev); ol = torch.empty(m, dtype=torch.int32, device=dev)
+    uv = torch.empty((m, 2), dtype=torch.float64, device=dev); cl = torch.empty(m, dtype=torch.int32, device=dev)
+    if m:
+        capi.check(L.stba_visibility(*args, m, C.byref(n), _tptr(lm_deg, C.c_int32), _tptr(cam_deg, C.c_int32), _tptr(oc, C.c_int32),
+                                     _tptr(ol, C.c_int32), _tptr(uv, C.c_double), _tptr(cl, C.c_int32)), "stba_visibility")
+    return dict(lm_deg=lm_deg, cam_deg=cam_deg, obs_cam=oc, obs_lm=ol, obs_uv=uv, cam_lm=cl)
+
+
+def triangulate_device(cam_q, cam_t, lm0, obs_cam, obs_lm, obs_uv, options=None):
+    """Device hand-off form of `triangulate` (torch CUDA tensors).  Returns (lm, iterations, final_cost, termination, kernel_ms),
+    the per-landmark outputs as CUDA tensors."""
+    import torch
+    L = capi.lib()
+    dev = cam_q.device
+    n_cam, n_lm, n_obs = cam_q.shape[0], lm0.shape[0], obs_cam.shape[0]
+    lm = lm0.clone().contiguous()
+    its = torch.empty(n_lm, dtype=torch.int32, device=dev); cost = torch.empty(n_lm, dtype=torch.float64, device=dev)
+    term = torch.empty(n_lm, dtype=torch.int32, device=dev); ms = C.c_float(0)
+    capi.check(L.stba_triangulate(dev.index or 0, n_cam, n_lm, n_obs, _tptr(cam_q.contiguous(), C.c_double), _tptr(cam_t.contiguous(), C.c_double),
+                                  _tptr(lm, C.c_double), _tptr(obs_cam.contiguous(), C.c_int32), _tptr(obs_lm.contiguous(), C.c_int32),
+                                  _tptr(obs_uv.contiguous(), C.c_double), C.byref(options) if options is not None else None,
+                                  _tptr(its, C.c_int32), _tptr(cost, C.c_double), _tptr(term, C.c_int32), C.byref(ms)), "stba_triangulate")
+    return lm, its, cost, term, float(ms.value)
+
+
 PNP_JACOBIAN_REFERENCE, PNP_JACOBIAN_EXACT = 0, 1
 
 

@@ -247,3 +247,38 @@ def test_pnp_gauss_newton_kernel_equals_the_reference_self_gauss_newton(stba):
     assert np.abs(qb[0] - q).max() < 1e-15 and ib[0] == its and ib[2] <= 1
     for k in range(3):
         assert min(np.abs(qb[k] - s["q_real"]).max(), np.abs(qb[k] + s["q_real"]).max()) < 1e-7 and np.abs(tb[k] - s["t_real"]).max() < 1e-7
+
+
+@pytest.mark.gpu
+def test_device_hand_off_visibility_triangulate_ba(stba):
+    """The three stages chained through DEVICE memory (torch CUDA tensors as the C ABI's array arguments): same
+    index lists (bit-exact), same triangulated points and the same LM solve as the host-buffer route."""
+    import torch
+    sc = stba.synth.make_scene(20, 300, 1200)
+    dev = torch.device("cuda", 0)
+    q = torch.as_tensor(sc.true_cam_q, device=dev); t = torch.as_tensor(sc.true_cam_t, device=dev); p = torch.as_tensor(sc.true_lm, device=dev)
+    vis_h = stba.front.visibility(sc.true_cam_q, sc.true_cam_t, sc.true_lm)
+    vis_d = stba.front.visibility_device(q, t, p)
+    for k in ("lm_deg", "cam_deg", "obs_cam", "obs_lm", "cam_lm"):
+        assert np.array_equal(vis_d[k].cpu().numpy(), vis_h[k]), k
+    assert np.array_equal(vis_d["obs_uv"].cpu().numpy(), vis_h["obs_uv"])
+    keep = vis_h["lm_deg"] >= 2                       # triangulation needs two rays
+    sel = keep[vis_h["obs_lm"]]
+    remap = np.cumsum(keep) - 1
+    oc = vis_h["obs_cam"][sel]; ol = remap[vis_h["obs_lm"][sel]].astype(np.int32); uv = vis_h["obs_uv"][sel]
+    lm0 = sc.true_lm[keep] + 0.05
+    lm_h, its_h, _, _, _ = stba.front.triangulate(sc.true_cam_q, sc.true_cam_t, lm0, oc, ol, uv)
+    d_oc = torch.as_tensor(oc, device=dev); d_ol = torch.as_tensor(ol, device=dev); d_uv = torch.as_tensor(uv, device=dev)
+    lm_d, its_d, _, _, _ = stba.front.triangulate_device(q, t, torch.as_tensor(lm0, device=dev), d_oc, d_ol, d_uv)
+    assert np.array_equal(its_d.cpu().numpy(), its_h)
+    assert np.array_equal(lm_d.cpu().numpy(), lm_h)
+    cc = np.zeros(20, np.uint8); cc[0] = cc[-1] = 1
+    q0 = torch.as_tensor(sc.cam_q, device=dev); t0 = torch.as_tensor(sc.cam_t, device=dev)
+    e_d = stba.engine.BAEngine.from_device(q0, t0, lm_d, d_oc, d_ol, d_uv, cam_const=cc)
+    e_h = stba.engine.BAEngine(sc.cam_q, sc.cam_t, lm_h, oc, ol, uv, cam_const=cc)
+    s_d = e_d.solve(); s_h = e_h.solve()
+    assert len(s_d.iterations) == len(s_h.iterations) and s_d.final_cost == s_h.final_cost
+    qd, td, pd = e_d.get_state_device()
+    qh, th, ph = e_h.get_state()
+    assert np.array_equal(qd.cpu().numpy(), qh) and np.array_equal(pd.cpu().numpy(), ph)
+    e_d.close(); e_h.close()
