@@ -138,6 +138,10 @@ struct Engine {
   // the cached linearisation) gives the same result.
   double* red = nullptr;
   size_t red_count = 0, off_rhs = 0, off_hcc = 0, off_gc = 0, off_tail = 0;
+  static constexpr int kMaxRedChunks = 8;
+  int red_chunks = getenv("STBA_RED_CHUNKS") ? std::max(1, std::min(kMaxRedChunks, atoi(getenv("STBA_RED_CHUNKS")))) : 4;
+  cudaStream_t cstream = nullptr;                 // communication stream of the chunked reduction
+  cudaEvent_t cev[kMaxRedChunks + 1] = {};
   double radius_built = 0.0;
   bool want_xnorm = false;
   const double* Hcc_use() const { return nranks > 1 ? red + off_hcc : Hcc; }
@@ -185,6 +189,9 @@ struct Engine {
     if (scal_host) { std::lock_guard<std::mutex> lk(g_pinned_mu); g_pinned_free.push_back(scal_host); }
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
+    for (auto& e : cev)
+      if (e) cudaEventDestroy(e);
+    if (cstream) cudaStreamDestroy(cstream);
     if (comm && comm_owned) ncclCommDestroy(comm);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -540,7 +547,7 @@ int Engine::build_reduced(double radius, const stba_options& opt) {
     if (n_chunk)
       LAUNCH(this, k_schur_diag, n_chunk, 32, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
     LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, S, ld, rhs, 1, 0);
-    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, S, ld, 0);
+    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, (int64_t)0, n_blk, blk_ptr, inc, E, S, ld, 0);
   }
   CK(cudaGetLastError());
   reduced_built = true;
@@ -566,7 +573,6 @@ int Engine::reduce_linearization(double radius, const stba_options& opt) {
     if (n_chunk) LAUNCH(this, k_schur_diag, n_chunk, 32, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
     LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, red, ld,
            red + off_rhs, 0, 1);
-    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, n_blk, blk_ptr, inc, E, red, ld, 1);
   }
   if (n_cam) {
     CK(cudaMemcpyAsync(red + off_hcc, Hcc, 21 * (size_t)n_cam * sizeof(double), cudaMemcpyDeviceToDevice, stream));
@@ -577,7 +583,36 @@ int Engine::reduce_linearization(double radius, const stba_options& opt) {
   if (want_xnorm)
     LAUNCH(this, k_x_norm, grid_for(n_lm, kBlock), kBlock, 0, n_lm, cam_const, lc, cam_q, cam_t, lm4, partial, counter, scal + SC_XNORM2);
   LAUNCH(this, k_fill_tail, 1, 32, tail, rank, scal, (int)SC_COST, (int)SC_G2, (int)SC_GMAX, (int)SC_XNORM2);
-  CKN(ncclAllReduce(red, red, red_count, ncclDouble, ncclSum, comm, stream));
+  // The off-diagonal blocks — the bulk of the buffer — are produced block-row range by block-row range (row-major packed:
+  // a range of rows is a contiguous range of the buffer); each finished range is all-reduced on the communication
+  // stream while the next one is computed.  Still ONE logical reduction of [S | rhs | H_cc | g_c | scalars] per
+  // linearisation: the last range carries everything behind S.
+  const int n_rng = (n_blk && red_chunks > 1 && n_free >= 64) ? red_chunks : 1;
+  if (n_rng == 1) {
+    if (n_free && n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, (int64_t)0, n_blk, blk_ptr, inc, E, red, ld, 1);
+    CKN(ncclAllReduce(red, red, red_count, ncclDouble, ncclSum, comm, stream));
+  } else {
+    if (!cstream) {
+      CK(cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));
+      for (auto& e2 : cev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    }
+    int i_prev = 0;
+    for (int c = 0; c < n_rng; ++c) {
+      // equal shares of the triangle: row boundary at n_free sqrt((c + 1) / n_rng), on a multiple of 16 cameras
+      int i_end = (c + 1 == n_rng) ? n_free : (int)(n_free * std::sqrt((double)(c + 1) / n_rng)) / 16 * 16;
+      i_end = std::max(i_end, i_prev);
+      const int64_t b0 = (int64_t)i_prev * (i_prev - 1) / 2, b1 = (int64_t)i_end * (i_end - 1) / 2;
+      if (b1 > b0) LAUNCH(this, k_schur_off, grid_for(b1 - b0, kBlock), kBlock, b0, b1, blk_ptr, inc, E, red, ld, 1);
+      CK(cudaEventRecord(cev[c], stream));
+      CK(cudaStreamWaitEvent(cstream, cev[c], 0));
+      const size_t r0 = 6 * (size_t)i_prev, r1 = 6 * (size_t)i_end;
+      const size_t e0 = r0 * (r0 + 1) / 2, e1 = (c + 1 == n_rng) ? red_count : r1 * (r1 + 1) / 2;
+      if (e1 > e0) CKN(ncclAllReduce(red + e0, red + e0, e1 - e0, ncclDouble, ncclSum, comm, cstream));
+      i_prev = i_end;
+    }
+    CK(cudaEventRecord(cev[kMaxRedChunks], cstream));
+    CK(cudaStreamWaitEvent(stream, cev[kMaxRedChunks], 0));
+  }
   // ---- on the reduced values (replicated work, bit-identical on every rank) ----
   if (first && n_cam) LAUNCH(this, k_jacobi_scale, (n_cam + 127) / 128, 128, n_cam, 0, opt.jacobi_scaling, Hcc_use(), nullptr, sc, sl);
   have_scale = true;

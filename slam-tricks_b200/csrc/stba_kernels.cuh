@@ -281,9 +281,11 @@ __global__ void k_add_cam_blocks(int n_cam, const int* __restrict__ free_of, con
 // indices of one landmark seen by both cameras) is static and sorted, so the sum order is fixed:
 // no atomics, no zero-fill, every block written exactly once.
 __global__ void __launch_bounds__(kBlock)
-k_schur_off(int64_t n_blk, const int64_t* __restrict__ blk_ptr, const uint64_t* __restrict__ inc,
+k_schur_off(int64_t b_begin, int64_t n_blk, const int64_t* __restrict__ blk_ptr, const uint64_t* __restrict__ inc,
             const double* __restrict__ E, double* __restrict__ S, int n, int packed) {
-  for (int64_t b = (int64_t)blockIdx.x * kBlock + threadIdx.x; b < n_blk; b += (int64_t)gridDim.x * kBlock) {
+  // blocks [b_begin, n_blk): the multi-GPU path produces the packed buffer block-row range by block-row range so that
+  // the all-reduce of a finished range overlaps the computation of the next one
+  for (int64_t b = b_begin + (int64_t)blockIdx.x * kBlock + threadIdx.x; b < n_blk; b += (int64_t)gridDim.x * kBlock) {
     // b = i (i-1) / 2 + j,  i > j >= 0
     int64_t i = (int64_t)((1.0 + sqrt(1.0 + 8.0 * (double)b)) * 0.5);
     while (i * (i - 1) / 2 > b) --i;
