@@ -547,7 +547,10 @@ __device__ __forceinline__ void st_release(int* p, int v) {
 
 __global__ void __launch_bounds__(TBA_THREADS, 1)
 k_trsv_bwd_all(const double* __restrict__ S, int ld, int n, int T, const double* __restrict__ Linv, const double* __restrict__ y,
-               double* x, int* flags, int* __restrict__ info, int blk0) {
+               double* x, int* flags, int* __restrict__ info, int blk0, int poll_data = 0) {
+  // poll_data: x was pre-filled with NaNs (0xFF bytes); every element is its own "ready" flag — the consumers spin
+  // on the values themselves (one L2 round trip per hop instead of flag + data) and the producer needs neither a
+  // fence nor a flag store.  8-byte stores are single-copy atomic; a NaN solution only occurs after info != 0.
   extern __shared__ __align__(16) double sm[];
   double* Lb = sm;                          // Lb[c * NB + r] = L(k0 + r, j0 + c)
   double* U = Lb + NB * NB;                 // U[c (c + 1) / 2 + r] = Linv_jj(c, r), r <= c
@@ -579,14 +582,30 @@ k_trsv_bwd_all(const double* __restrict__ S, int ld, int n, int T, const double*
       }
     }
     cp_async_commit();
-    if (t == 0) {
-      long long spins = 0;
-      while (ld_acquire(flags + k) == 0) {
-        if (++spins > (1ll << 26)) { atomicCAS(info, 0, -1); break; }    // never hang the device
+    if (poll_data) {
+      if (t < NB) {
+        double v = 0.0;
+        if (t < nbk) {
+          long long spins = 0;
+          const volatile double* src = x + k0 + t;
+          for (;;) {
+            v = *src;
+            if (v == v) break;
+            if (++spins > (1ll << 24)) { atomicCAS(info, 0, -1); v = 0.0; break; }    // never hang the device
+          }
+        }
+        xk[t] = v;
       }
+    } else {
+      if (t == 0) {
+        long long spins = 0;
+        while (ld_acquire(flags + k) == 0) {
+          if (++spins > (1ll << 26)) { atomicCAS(info, 0, -1); break; }    // never hang the device
+        }
+      }
+      __syncthreads();
+      if (t < NB) xk[t] = (t < nbk) ? __ldcg(x + k0 + t) : 0.0;
     }
-    __syncthreads();
-    if (t < NB) xk[t] = (t < nbk) ? __ldcg(x + k0 + t) : 0.0;
     cp_async_wait<0>();
     __syncthreads();
     const double x0 = xk[lane], x1 = xk[lane + 32], x2 = xk[lane + 64], x3 = xk[lane + 96];
@@ -615,8 +634,13 @@ k_trsv_bwd_all(const double* __restrict__ S, int ld, int n, int T, const double*
     __syncthreads();
     if (h == 1) xk[r] = s0 + s1;
     __syncthreads();
-    if (h == 0 && j0 + r < n) x[j0 + r] = (s0 + s1) + xk[r];
+    if (h == 0 && j0 + r < n) {
+      double v = (s0 + s1) + xk[r];
+      if (poll_data && !(v == v)) { atomicCAS(info, 0, -1); v = 0.0; }      // a NaN would read as "not ready" downstream
+      x[j0 + r] = v;
+    }
   }
+  if (poll_data) return;
   __threadfence();
   __syncthreads();
   if (t == 0) st_release(flags + j, 1);
@@ -2826,9 +2850,9 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
   void* args[] = {&dp};
   CKC(cudaLaunchCooperativeKernel((const void*)k_chol_dag2, dim3(P.grid), dim3(DAG_THREADS), args, DAG_SMEM, stream));
   k_get_row<<<(n + 255) / 256, 256, 0, stream>>>(P.S, ld, n, P.ybuf);
-  CKC(cudaMemsetAsync(P.flags, 0, (size_t)T * sizeof(int), stream));
+  CKC(cudaMemsetAsync(P.rhs, 0xFF, (size_t)n * sizeof(double), stream));      // NaN = "not computed yet" (k_trsv_bwd_all, poll_data)
   for (int b0 = 0; b0 < T; b0 += substitution_chunk())
-    k_trsv_bwd_all<<<std::min(T - b0, substitution_chunk()), TBA_THREADS, TBA_SMEM, stream>>>(P.S, ld, n, T, P.Linv, P.ybuf, P.rhs, P.flags, P.info, b0);
+    k_trsv_bwd_all<<<std::min(T - b0, substitution_chunk()), TBA_THREADS, TBA_SMEM, stream>>>(P.S, ld, n, T, P.Linv, P.ybuf, P.rhs, P.flags, P.info, b0, 1);
   CKC(cudaGetLastError());
   P.launches = 4;
   if (P.prof) {
