@@ -145,6 +145,10 @@ int stba_peak_fp64(int device, int reps, double* tflops);
 /* obs_cam i32[n_obs], obs_lm i32[n_obs] (non-decreasing = landmark-major,               */
 /* test_ceres.h:109-110), obs_uv f64[n_obs,2], cam_const u8[n_cam], lm_const u8[n_lm]    */
 /* (NULL = all free; all-constant landmarks = the PnP problem of solver.hpp:247-385).    */
+/* cam_q, cam_t, lm, obs_cam, obs_lm, obs_uv may be HOST or DEVICE pointers (unified       */
+/* addressing; device arrays are copied device-to-device and validated on the device);    */
+/* cam_const / lm_const are host arrays.  The same holds for set_state / get_state and    */
+/* for the array arguments of stba_visibility / stba_triangulate below.                   */
 /* ==================================================================================== */
 typedef struct stba_ba stba_ba;
 
