@@ -302,7 +302,8 @@ constexpr int POTRF_SMEM = (NB * PLD + NB + 32 * TLD + 32 * 33) * (int)sizeof(do
 constexpr unsigned FULL = 0xffffffffu;
 #ifdef STBA_CHOL_TIMING
 __device__ long long g_potrf_clk[64];
-#define TICK(i) do { if (threadIdx.x == 0) g_potrf_clk[i] = clock64(); } while (0)
+__device__ int g_tick_k0 = -1;      // panel whose phases are recorded (-1: every panel, i.e. the last one survives)
+#define TICK(i) do { if (threadIdx.x == 0 && (g_tick_k0 < 0 || g_tick_k0 == k0)) g_potrf_clk[i] = clock64(); } while (0)
 #else
 #define TICK(i) do {} while (0)
 #endif
@@ -877,7 +878,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 //     inverts the 32 x 32 diagonal factor blocks as they appear and publishes them (pinv): the consumers of
 //     the panel (the solve of the next tile row) start on block column b while b + 1 is being factored.
 constexpr int QLD = NB + 4;      // (q QLD + g) mod 16 distinct over a half-warp: conflict-free DMMA fragments
-constexpr int PROG_SMEM = (NB * QLD + NB + 32 * 32 + 32 * QLD) * (int)sizeof(double);
+constexpr int PROG_SMEM = (NB * QLD + NB + 32 * 32 + 2 * 32 * QLD) * (int)sizeof(double);
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 480;" ::: "memory"); }
 
@@ -929,30 +930,54 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
     // ---- the LAST update of this tile, A_kk -= X X^T with X = L(k, k-1), applied here while the solve of tile row k
     //      against panel k-1 is still publishing its block columns (xflag >= xbase + b + 1): the tile never makes the
     //      round trip  update CTA -> global memory -> flag -> this CTA  between the last solve step and the first pivot
-    for (int b = 0; b < 4; ++b) {
+    // Two buffers: the block column b + 1 is fetched (cp.async) while block column b is applied, if it has been published
+    // already — in the steady state all but the last one have, long before this CTA gets here.
+    int have = 0, avail = 0;          // block columns whose load has been issued / that are known to be published (CTA-uniform)
+    // the flags are polled only when the next block column is not yet known to be there: a poll costs L2 round trips,
+    // and in the steady state all four have been published long before this CTA gets here
+    auto poll = [&](int want) {
       if (tid == 0) {
         long long spins = 0;
-        while (ld_relaxed(xflag) < xbase + b + 1 || (xflag2 && ld_relaxed(xflag2) < xbase + b + 1)) {
-          if ((++spins & 255) == 0 && abort_flag && ld_relaxed(abort_flag)) break;
-          if (spins > (1ll << 21)) break;
+        int v = 0;
+        for (;;) {
+          v = ld_relaxed(xflag) - xbase;
+          if (xflag2) v = min(v, ld_relaxed(xflag2) - xbase);
+          if (v >= want) break;
+          if ((++spins & 255) == 0 && abort_flag && ld_relaxed(abort_flag)) { v = 4; break; }
+          if (spins > (1ll << 21)) { v = 4; break; }
         }
-        ld_acquire_gpu(xflag);
-        if (xflag2) ld_acquire_gpu(xflag2);
+        __threadfence();
+        *s_sig = min(v, 4);
       }
       __syncthreads();
+      avail = *s_sig;
+      __syncthreads();
+    };
+    auto issue = [&]() {
+      double* Xd = Xb + (have & 1) * 32 * QLD;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int e = tid + i * 512;
         const int c = e >> 6, r2 = (e & 63) * 2;
-        const double* src = S + (size_t)(k0 - NB + 32 * b + c) * ld + k0 + r2;
-        double2 v = make_double2(0.0, 0.0);
-        if (r2 + 1 < nb) v = __ldcg(reinterpret_cast<const double2*>(src));
-        else if (r2 < nb) v.x = __ldcg(src);
-        Xb[c * QLD + r2] = v.x;
-        Xb[c * QLD + r2 + 1] = v.y;
+        const double* src = S + (size_t)(k0 - NB + 32 * have + c) * ld + k0 + r2;
+        if (r2 + 1 < nb) {
+          cp_async16(Xd + c * QLD + r2, src, true);
+        } else {
+          Xd[c * QLD + r2] = (r2 < nb) ? __ldcg(src) : 0.0;
+          Xd[c * QLD + r2 + 1] = 0.0;
+        }
       }
+      cp_async_commit();
+      ++have;
+    };
+    poll(1);
+    issue();
+    for (int b = 0; b < 4; ++b) {
+      if (have == b + 1 && have < avail) issue();          // next block column already published: fetch it behind this one
+      if (have == b + 2) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncthreads();
       {
+        const double* Xc = Xb + (b & 1) * 32 * QLD;
         int cnt = 0;
         for (int ti = 0; ti < 8; ++ti)
           for (int tj = 0; tj <= ti; ++tj, ++cnt) {
@@ -967,7 +992,7 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
                 for (int e = 0; e < 2; ++e) acc[mi][ni][e] = D[(c0 + 8 * ni + 2 * q + e) * QLD + r0 + 8 * mi + g];
 #pragma unroll
             for (int kk = 0; kk < 32; kk += 4) {
-              const double* colp = Xb + (kk + q) * QLD;
+              const double* colp = Xc + (kk + q) * QLD;
               const double a0 = -colp[r0 + g], a1 = -colp[r0 + 8 + g];
               const double bb0 = colp[c0 + g], bb1 = colp[c0 + 8 + g];
               dmma(acc[0][0][0], acc[0][0][1], a0, bb0);
@@ -984,6 +1009,7 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
           }
       }
       __syncthreads();
+      if (have == b + 1 && b + 1 < 4) { poll(have + 1); issue(); }
     }
     // the right-hand-side row (row n of S) lives inside the last diagonal tile when n is not a multiple of 128: its
     // share of this update, one thread per column
@@ -996,6 +1022,7 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
       }
       S[(size_t)(k0 + tid) * ld + rr] -= acc;
     }
+    if (tid == 0) *s_sig = 0;       // (borrowed as the broadcast slot of try_issue)
     __syncthreads();
   }
   TICK(1);
@@ -1079,17 +1106,11 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const double v = (c == lane) ? dl * rsl : a[c] * xd[b0 + c];
-          a[c] = v;
           if (c <= lane) D[(b0 + c) * QLD + b0 + lane] = v;
         }
         __threadfence_block();
         __syncwarp();
         if (lane == 0) *s_sig = b + 1;
-        // the finished rows go straight to global memory (one 256-byte segment per column and warp): no copy-out
-        // pass between "block column b factored" and "block column b published"
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c <= lane && b0 + lane < nb) S[(size_t)(k0 + b0 + c) * ld + k0 + b0 + lane] = a[c];
         TICK(20 + b);
       } else if (warp > b && warp < 4) {
         // (2) rows below the pivot block follow the same elimination, four columns behind at most: the former
@@ -1118,21 +1139,29 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
         while (*s_prog < base + 33) { }
         __threadfence_block();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const double v = a[c] * xd[b0 + c];
-          D[(b0 + c) * QLD + r] = v;
-          if (r < nb && b0 + c < nb) S[(size_t)(k0 + b0 + c) * ld + k0 + r] = v;
-        }
+        for (int c = 0; c < 32; ++c) D[(b0 + c) * QLD + r] = a[c] * xd[b0 + c];
       }
       bar_workers();
       TICK(2 + 3 * b);
       TICK(3 + 3 * b);
       const int below = NB - b0 - 32;
-      if (warp == 14) {
-        // block column b is final and on its way to global memory: the stores of the warps that own its rows
-        // happen before this point (barrier), the fence below is cumulative (the grid-sync idiom): publish it
+      // Block column b is final: copy it out (direct stores from the row-owning warps were measured and cost 3-4 k
+      // cycles per block on the pivot phase: profiles/r2_dense_notes.md).  While the other warps run the rank-32 update,
+      // warp 14 copies and publishes; after the last block there is nothing to update and all 15 warps share the copy.
+      if (warp == 14 || below == 0) {
+        const int cstep = below == 0 ? 15 : 1, cfirst = below == 0 ? warp : 0;
+        for (int c = b0 + cfirst; c < b0 + 32 && c < nb; c += cstep) {
+          double* dst = S + (size_t)(k0 + c) * ld + k0;
+          const double* srcc = D + c * QLD;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = b0 + lane + 32 * i;
+            if (r >= c && r < nb) dst[r] = srcc[r];
+          }
+        }
         __threadfence();
-        if (lane == 0) st_release_gpu(pb_flag, b + 1);
+        __syncwarp();
+        if (below > 0 && lane == 0) st_release_gpu(pb_flag, b + 1);
       } else if (below > 0) {
         // (3) rank-32 update of the remaining lower triangle on the FP64 tensor pipe: 16 x 16 macro tiles (four
         //     independent accumulator pairs hide the DMMA latency), lower triangle of the (below / 16)^2 grid
@@ -1169,6 +1198,7 @@ __device__ __forceinline__ void potrf128_prog_dev(double* __restrict__ S, int ld
           }
       }
       bar_workers();
+      if (below == 0 && warp == 14 && lane == 0) st_release_gpu(pb_flag, b + 1);      // every warp's share is stored and fenced
       TICK(4 + 3 * b);
     }
   }
@@ -1893,6 +1923,12 @@ __device__ __forceinline__ int* f2_sv(const Dag2Params& P) { return f2_xpub(P) +
 __device__ __forceinline__ int* f2_st(const Dag2Params& P) { return f2_sv(P) + P.R64; }
 __device__ __forceinline__ int* f2_hd(const Dag2Params& P) { return f2_st(P) + (size_t)P.Tr * P.T; }
 __device__ __forceinline__ bool half2_exists(const Dag2Params& P, int h) { return h * 64 < P.n_rows; }
+// Panels the WORKERS owe tile (i, j): panels k >= i - D belong to the dedicated CTAs; with D = 1 the solve CTAs of tile
+// row j + 1 also apply the last update (panel j - 1) of their own tile (j + 1, j) themselves (solve_row_dev).
+__device__ __forceinline__ int lim2(const Dag2Params& P, int i, int j) {
+  const int l = min(j, i - P.D);
+  return (P.D == 1 && i - j == 1) ? l - 1 : l;
+}
 
 __device__ __forceinline__ void dag2_abort(const Dag2Params& P) {
   atomicCAS(P.info, 0, -1);
@@ -1955,7 +1991,7 @@ __device__ __forceinline__ bool wait3(const Dag2Params& P, const int* f0, const 
     long long spins = 0;
     int ok = 1;
     for (;;) {
-      if ((!f0 || ld_relaxed(f0) >= v) && (!f1 || ld_relaxed(f1) >= v) && (!f2 || ld_relaxed(f2) >= v)) {
+      if ((!f0 || (ld_relaxed(f0) & ~ST_LOCK) >= v) && (!f1 || (ld_relaxed(f1) & ~ST_LOCK) >= v) && (!f2 || (ld_relaxed(f2) & ~ST_LOCK) >= v)) {      // (sv counters carry a lock bit while a panel solve is running)
         if (f0) ld_acquire_gpu(f0);
         if (f1) ld_acquire_gpu(f1);
         if (f2) ld_acquire_gpu(f2);
@@ -1989,8 +2025,12 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int ha
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   int* sv = f2_sv(P);
   if (trace_base >= 0) TRACE(P, k, trace_base);
-  // tile (i, k) has received every update (panels 0 .. k-1)
-  if (!wait2(P, f2_st(P) + (size_t)i * T + k, k, nullptr, 0, s_ok, prof)) return false;
+  // With D = 1 the LAST update of tile (k + 1, k) (panel k - 1) is applied right here instead of by a worker: on the
+  // chain's cycle it replaced  [worker scan -> 128 x 128 x 128 update, 24 us -> flag -> this CTA]  by 64 rows of that
+  // update on this SM, started the moment L(k + 1, k - 1) exists.
+  const bool own_last = P.D == 1 && i == k + 1 && k >= 1;
+  // tile (i, k) has received every update the workers owe it
+  if (!wait2(P, f2_st(P) + (size_t)i * T + k, own_last ? k - 1 : k, nullptr, 0, s_ok, prof)) return false;
   if (trace_base >= 0) TRACE(P, k, trace_base + 1);
   const long long c_begin = clock64();
   for (int c = warp; c < NB; c += 16) {
@@ -2005,6 +2045,58 @@ __device__ __forceinline__ bool solve_row_dev(const Dag2Params& P, int i, int ha
     }
   }
   cp_async_commit();
+  if (own_last) {
+    // X -= L(i, k-1)[my 64 rows] L(k, k-1)^T, K = 128 in four chunks of 32 (double-buffered cp.async stages in the part
+    // of shared memory the solve only uses later); all 16 warps: strip = warp & 7, column half = warp >> 3.
+    constexpr int ALD = 64 + 4, BLD = NB + 4, STG = 32 * (ALD + BLD);
+    double* stg = sm + 8 * NB * 8;
+    const int kp0 = (k - 1) * NB, rk0 = k * NB;
+    // L(i, k-1) of these rows (panel solve by a worker) and L(k, k-1) (both halves, the previous step of the solve CTAs)
+    if (!wait3(P, sv + 2 * i + half, sv + 2 * k, half2_exists(P, 2 * k + 1) ? sv + 2 * k + 1 : nullptr, k, s_ok, prof)) return false;
+    auto load_chunk = [&](int c4, int stage) {
+      double* As = stg + stage * STG;
+      double* Bs = As + 32 * ALD;
+#pragma unroll
+      for (int p = 0; p < 32 * 64 / DAG_THREADS; ++p) {
+        const int piece = tid + p * DAG_THREADS;
+        const int kk = piece >> 6, r2 = (piece & 63) * 2;
+        const double* colp = S + (size_t)(kp0 + 32 * c4 + kk) * ld;
+        const int ra = r0 + r2, rb = rk0 + r2;
+        if (r2 < 64) cp_async16(As + kk * ALD + r2, colp + (ra < n_rows ? ra : 0), ra < n_rows);
+        cp_async16(Bs + kk * BLD + r2, colp + (rb < n_rows ? rb : 0), rb < n_rows);
+      }
+      cp_async_commit();
+    };
+    load_chunk(0, 0);
+    cp_async_wait<1>();          // the X strips (first group) have landed
+    __syncthreads();
+    const int strip = warp & 7, ch = warp >> 3;
+    double* Xq = Xs + strip * NB * 8;
+    double acc[8][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) acc[nt][e] = Xq[(64 * ch + 8 * nt + 2 * q + e) * 8 + g];
+    for (int c4 = 0; c4 < 4; ++c4) {
+      if (c4 + 1 < 4) load_chunk(c4 + 1, (c4 + 1) & 1);
+      if (c4 + 1 < 4) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncthreads();
+      const double* As = stg + (c4 & 1) * STG + strip * 8 + g;
+      const double* Bs = stg + (c4 & 1) * STG + 32 * ALD + 64 * ch + g;
+#pragma unroll
+      for (int kk = 0; kk < 32; kk += 4) {
+        const double a = -As[(kk + q) * ALD];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) dmma(acc[nt][0], acc[nt][1], a, Bs[(kk + q) * BLD + 8 * nt]);
+      }
+      __syncthreads();           // the stage is refilled two chunks later
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) Xq[(64 * ch + 8 * nt + 2 * q + e) * 8 + g] = acc[nt][e];
+    __syncthreads();
+  }
   const bool cw = warp < 8;             // 64 rows = 8 strips: warps 8..15 only help with the loads and the barriers
   double* Xw = Xs + (warp & 7) * NB * 8;
   const int row = r0 + (warp & 7) * 8 + g;
@@ -2293,7 +2385,7 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = ti[u], j = tj[u];
-          if (i >= 0 && (ta[u] & ~ST_LOCK) < min(j, i - P.D)) jinc = min(jinc, j);
+          if (i >= 0 && (ta[u] & ~ST_LOCK) < lim2(P, i, j)) jinc = min(jinc, j);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -2302,7 +2394,7 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
           int nk = 0;
           const int i = ti[u], j = tj[u], a = ta[u];
           if (i >= 0 && !(a & ST_LOCK)) {
-            const int lim = min(j, i - P.D);      // panels k >= i - D of tile (i, j) belong to the dedicated CTAs
+            const int lim = lim2(P, i, j);
             const int av = min(min(s_rowsv[i], s_rowsv[j]), lim);
             nk = min(av - a, P.G);
             if (nk > 0) {
@@ -2362,7 +2454,12 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
     if (claimed) break;
     if (ld_relaxed(P.flags + F2_DONE) >= P.total_units) break;
     if (++spins > (SPIN_LIMIT >> 3)) { if (lane == 0) dag2_abort(P); break; }
-    __nanosleep(200);
+    // Nothing ready.  In the tail of the factorisation a handful of tasks exist at any time and ~140 idle workers
+    // scanning and CAS-ing the same few words slow down the ones that matter: back off, the more the longer nothing
+    // was found, and park the workers the remaining trailing matrix (< (T - np)^2 tiles) cannot employ anyway.
+    const int rem = max(T - np, 1);
+    const bool surplus = wid >= 8 + 2 * rem * rem;
+    __nanosleep(surplus ? 3000 : min(200u << min(spins, 4ll), 1600u));
   }
   __threadfence();
   if (lane == 0) *t_wait += clock64() - c0;
@@ -2801,7 +2898,7 @@ static int build_dag2_plan(CholPlan& P, cudaStream_t stream) {
     col_start[j] = (int)tiles.size();
     for (int i = j; i < P.Tr; ++i) {
       tiles.push_back(i | (j << 16));
-      units += std::max(std::min(j, i - P.D), 0);      // panels k >= i - D of tile (i, j) belong to the dedicated CTAs
+      units += std::max(std::min(j, i - P.D) - ((P.D == 1 && i - j == 1) ? 1 : 0), 0);      // = lim2() of the kernel
     }
   }
   col_start[T] = (int)tiles.size();
@@ -2883,6 +2980,8 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
     }
 #ifdef STBA_CHOL_TIMING
     {
+      static bool tick_set = false;
+      if (!tick_set) { int v = getenv("STBA_TICK_K0") ? atoi(getenv("STBA_TICK_K0")) : -1; cudaMemcpyToSymbol(g_tick_k0, &v, sizeof(int)); tick_set = true; }
       long long hc[64];
       cudaMemcpyFromSymbol(hc, g_potrf_clk, sizeof(hc));
       fprintf(stderr, "[potrf128 clocks, last panel]");
