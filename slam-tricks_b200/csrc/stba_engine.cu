@@ -21,6 +21,7 @@
 #include "stba_chol.cuh"
 #include "stba_kernels.cuh"
 #include "stba_lin.cuh"
+#include "stba_lin3.cuh"
 
 namespace stba {
 
@@ -110,6 +111,10 @@ struct Engine {
   int* free_of = nullptr;
   int *chunk_cam = nullptr, *chunk_beg = nullptr, *chunk_end = nullptr, *cam_chunk_ptr = nullptr;
   unsigned int* cam_ticket = nullptr;   // per-camera arrival counters of lin_cam2 (self re-arming)
+  int4* ctab = nullptr;                 // k_lin3: chunk table of the landmark group
+  unsigned int* cam_counter = nullptr;  // k_lin3: ticket counter of the camera-chunk queue (self re-arming)
+  int n_lm_chunks = 0;
+  bool use_lin3 = getenv("STBA_LIN2") == nullptr;   // STBA_LIN2=1: the three-launch linearisation of rounds 1-2 (yard-stick)
   int64_t* blk_ptr = nullptr;
   uint64_t* inc = nullptr;
   int* dup_flag = nullptr;
@@ -238,6 +243,8 @@ static int process_init(int device) {
   CK(cudaFuncSetAttribute(k_lin_lm2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmemBytes));
   CK(cudaFuncSetAttribute(k_lin_lm2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmemBytes));
   CK(cudaFuncSetAttribute(k_lin_lm2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinSmemBytes));
+  CK(cudaFuncSetAttribute(k_lin3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL3SmemBytes));
+  CK(cudaFuncSetAttribute(k_lin3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL3SmemBytes));
   d.ready = true;
   return STBA_OK;
 }
@@ -310,7 +317,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CKR(alloc(&Rt, kCamTile * (size_t)ncam)); CKR(alloc(&Rt2, kCamTile * (size_t)ncam));
   CKR(alloc(&obs_cam, (size_t)nobs + 8));   // +8: bulk copies round up to 16 B
   CKR(alloc(&obs_lm, (size_t)nobs)); CKR(alloc(&obs_uv, 2 * (size_t)nobs));
-  CKR(alloc(&lm_ptr, (size_t)nlm + 1)); CKR(alloc(&lm_deg, (size_t)nlm));
+  CKR(alloc(&lm_ptr, (size_t)nlm + 1 + 4)); /* +4: bulk copies round up to 16 B */ CKR(alloc(&lm_deg, (size_t)nlm));
   CKR(alloc(&cam_ptr, (size_t)ncam + 1)); CKR(alloc(&cam_deg, (size_t)ncam));
   CKR(alloc(&cam_perm, (size_t)nobs)); CKR(alloc(&cobs_lm, (size_t)nobs)); CKR(alloc(&cobs_uv, 2 * (size_t)nobs));
   CKR(alloc(&cam_const, (size_t)ncam)); CKR(alloc(&free_of, (size_t)ncam));
@@ -363,6 +370,11 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   }
   LAUNCH(this, (k_exclusive_scan<int, int>), 1, 1024, (int64_t)nlm, lm_deg, lm_ptr);
   LAUNCH(this, (k_exclusive_scan<int, int>), 1, 1024, (int64_t)ncam, cam_deg, cam_ptr);
+  n_lm_chunks = (nlm + kL3Lm - 1) / kL3Lm;
+  CKR(alloc(&ctab, (size_t)n_lm_chunks));
+  CKR(alloc(&cam_counter, 1));
+  CK(cudaMemsetAsync(cam_counter, 0, sizeof(unsigned int), stream));
+  if (n_lm_chunks) LAUNCH(this, k_l3_chunk_table, (n_lm_chunks + 3) / 4, 128, nlm, n_lm_chunks, lm_ptr, obs_cam, ctab);
   if (nobs) {
     int* cursor = nullptr;
     CKR(alloc(&cursor, (size_t)ncam));
@@ -496,6 +508,28 @@ int Engine::launch_lin_cam() {
 
 // residual + Jacobian + J^T J / J^T r blocks at the current x
 int Engine::linearize() {
+  if (nranks > 1 && n_cam && use_lin3) {   // cameras without local observations must not keep last iteration's reduced sums
+    CK(cudaMemsetAsync(Hcc, 0, 21 * (size_t)n_cam * sizeof(double), stream));
+    CK(cudaMemsetAsync(gc, 0, 6 * (size_t)n_cam * sizeof(double), stream));
+  }
+  if (use_lin3) {
+    // ONE launch: camera tiles + landmark-major pass + camera-major pass side by side on every SM (stba_lin3.cuh)
+    L3Params p;
+    p.n_lm = n_lm; p.n_cam = n_cam; p.n_lm_chunks = n_lm_chunks; p.n_cam_chunks = n_chunk;
+    p.lm_ptr = lm_ptr; p.obs_cam = obs_cam; p.obs_uv = obs_uv; p.lm4 = lm4; p.cam_q = cam_q; p.cam_t = cam_t;
+    p.ctab = ctab; p.Rt = Rt; p.Hll = Hll; p.gl = gl; p.partial = partial; p.counter = counter; p.out_cost = scal + SC_COST;
+    p.chunk_cam = chunk_cam; p.chunk_beg = chunk_beg; p.chunk_end = chunk_end; p.cam_chunk_ptr = cam_chunk_ptr;
+    p.cobs_lm = cobs_lm; p.cobs_uv = cobs_uv; p.chunk_acc = chunk_acc; p.cam_ticket = cam_ticket; p.Hcc = Hcc; p.gc = gc;
+    p.cam_counter = cam_counter;
+    const int grid = std::max(1, std::min(sm_count, std::max(n_lm_chunks, (n_chunk + kL3Threads / 32 - 1) / (kL3Threads / 32))));
+    if (n_cam <= kL3MaxCams) k_lin3<false><<<grid, kL3Threads, kL3SmemBytes, stream>>>(p);
+    else k_lin3<true><<<grid, kL3Threads, kL3SmemBytes, stream>>>(p);
+    ++launches;
+    CK(cudaGetLastError());
+    linearized = true;
+    reduced_built = false;
+    return STBA_OK;
+  }
   if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q, cam_t, Rt);
   // Two alternatives were measured and do not pay (profiles/r1_linearise_notes.md): the two passes on
   // two streams (lin_lm2 owns a whole SM's shared memory and 2/3 of its registers: 61.8 vs 62.3 us),
