@@ -114,6 +114,7 @@ struct Engine {
   int4* ctab = nullptr;                 // k_lin3: chunk table of the landmark group
   unsigned int* cam_counter = nullptr;  // k_lin3: ticket counter of the camera-chunk queue (self re-arming)
   int n_lm_chunks = 0;
+  bool rt_valid = false;                // Rt holds the tiles of (cam_q, cam_t): built on demand, swapped with Rt2 when a step is accepted
   bool use_lin3 = getenv("STBA_LIN2") == nullptr;   // STBA_LIN2=1: the three-launch linearisation of rounds 1-2 (yard-stick)
   int64_t* blk_ptr = nullptr;
   uint64_t* inc = nullptr;
@@ -389,12 +390,16 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CK(cudaMemcpyAsync(h_cam_ptr.data(), cam_ptr, ((size_t)ncam + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   {
-    // ~13 one-warp chunks per SM (about one round of the 16 resident warps), chunks between 64 and 2048
-    // observations (multiple of 32).  Measured at config C (tools/tune_cam_chunk.py): 160-observation
-    // chunks 33 us, 512 25 us, 1024 28 us — the per-chunk reduction + ticket are amortised over more
-    // observations while every SM still has a full set of warps.
-    int64_t target = nobs / ((int64_t)sm_count * 13) + 1;
-    chunk_size = (int)std::min<int64_t>(2048, std::max<int64_t>(64, (target + 31) / 32 * 32));
+    // One-warp chunks of whole 128-observation rounds (4 per lane), ~26 per SM: the camera group of k_lin3 pulls them
+    // from a ticket queue and the landmark warps join when their range is done, so chunks must be small enough to
+    // share (544-observation chunks left the landmark warps nothing to take: 41.3 us at C, 256: 39.5 us) and large
+    // enough to amortise the ~2.5 us of fold + fence + ticket per chunk; at 10 M observations one chunk per camera.
+    int64_t target = nobs / ((int64_t)sm_count * 26) + 1;
+    chunk_size = (int)std::min<int64_t>(2048, std::max<int64_t>(128, (target + 64) / 128 * 128));
+    if (!use_lin3) {      // the three-launch yard-stick keeps its own tuning (tools/tune_cam_chunk.py)
+      target = nobs / ((int64_t)sm_count * 13) + 1;
+      chunk_size = (int)std::min<int64_t>(2048, std::max<int64_t>(64, (target + 31) / 32 * 32));
+    }
     if (const char* ov = getenv("STBA_CAM_CHUNK")) chunk_size = std::max(32, atoi(ov) / 32 * 32);   // tuning experiments only
     std::vector<int> cc, cb, ce, ccp((size_t)ncam + 1, 0);
     for (int c = 0; c < ncam; ++c) {
@@ -470,6 +475,7 @@ int Engine::set_state(const double* h_q, const double* h_t, const double* h_lm) 
   CK(cudaStreamSynchronize(stream));
   linearized = false;
   reduced_built = false;
+  rt_valid = false;
   return STBA_OK;
 }
 
@@ -513,10 +519,12 @@ int Engine::linearize() {
     CK(cudaMemsetAsync(gc, 0, 6 * (size_t)n_cam * sizeof(double), stream));
   }
   if (use_lin3) {
-    // ONE launch: camera tiles + landmark-major pass + camera-major pass side by side on every SM (stba_lin3.cuh)
+    if (!rt_valid && n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q, cam_t, Rt);   // first linearisation / after set_state only
+    rt_valid = true;
+    // ONE launch: landmark-major pass + camera-major pass side by side on every SM (stba_lin3.cuh)
     L3Params p;
     p.n_lm = n_lm; p.n_cam = n_cam; p.n_lm_chunks = n_lm_chunks; p.n_cam_chunks = n_chunk;
-    p.lm_ptr = lm_ptr; p.obs_cam = obs_cam; p.obs_uv = obs_uv; p.lm4 = lm4; p.cam_q = cam_q; p.cam_t = cam_t;
+    p.lm_ptr = lm_ptr; p.obs_cam = obs_cam; p.obs_uv = obs_uv; p.lm4 = lm4;
     p.ctab = ctab; p.Rt = Rt; p.Hll = Hll; p.gl = gl; p.partial = partial; p.counter = counter; p.out_cost = scal + SC_COST;
     p.chunk_cam = chunk_cam; p.chunk_beg = chunk_beg; p.chunk_end = chunk_end; p.cam_chunk_ptr = cam_chunk_ptr;
     p.cobs_lm = cobs_lm; p.cobs_uv = cobs_uv; p.chunk_acc = chunk_acc; p.cam_ticket = cam_ticket; p.Hcc = Hcc; p.gc = gc;
@@ -531,6 +539,7 @@ int Engine::linearize() {
     return STBA_OK;
   }
   if (n_cam) LAUNCH(this, k_cam_prep, (n_cam + 127) / 128, 128, n_cam, cam_q, cam_t, Rt);
+  rt_valid = true;
   // Two alternatives were measured and do not pay (profiles/r1_linearise_notes.md): the two passes on
   // two streams (lin_lm2 owns a whole SM's shared memory and 2/3 of its registers: 61.8 vs 62.3 us),
   // and one fused persistent launch of k_cam_prep + lin_lm2 + lin_cam2 (60.3 vs 53.5 us: the camera-major
@@ -1152,6 +1161,12 @@ int stba_ba_time_phase(stba_ba* ba, int phase, int reps, int flush_l2, float* ms
 }
 
 
+#ifdef STBA_L3_TIMING
+extern "C" int stba_debug_l3_clocks(long long* out) {
+  return cudaMemcpyFromSymbol(out, stba::g_l3_clk, sizeof(long long) * 160 * 64) == cudaSuccess ? 0 : 2;
+}
+#endif
+
 int stba_ba_save_state(stba_ba* ba) {
   if (!ba) return STBA_ERR_INVALID_ARGUMENT;
   Engine& e = ba->e;
@@ -1171,7 +1186,7 @@ int stba_ba_restore_state(stba_ba* ba) {
   CK(cudaMemcpyAsync(e.cam_q, e.save_q, 4 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
   CK(cudaMemcpyAsync(e.cam_t, e.save_t, 3 * (size_t)e.n_cam * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
   CK(cudaMemcpyAsync(e.lm4, e.save_lm4, 4 * (size_t)e.n_lm * sizeof(double), cudaMemcpyDeviceToDevice, e.stream));
-  e.linearized = false; e.reduced_built = false;
+  e.linearized = false; e.reduced_built = false; e.rt_valid = false;
   return STBA_OK;
 }
 

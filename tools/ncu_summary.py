@@ -90,9 +90,13 @@ def traffic(path):
             tot += float(d[idx[m]].replace(",", "")) * scale[units[idx[m]]]
         per.setdefault(k, []).append(tot)
     kern = {k: sum(v) / len(v) for k, v in per.items()}
-    lin = sum(v for k, v in kern.items() if k.startswith("k_lin_lm2<0") or k.startswith("k_lin_cam2"))
+    lin3 = [v for k, v in kern.items() if k.startswith("k_lin3")]
+    if lin3:
+        lin, what = sum(lin3), "k_lin3"
+    else:
+        lin, what = sum(v for k, v in kern.items() if k.startswith("k_lin_lm2<0") or k.startswith("k_lin_cam2")), "k_lin_lm2 + k_lin_cam2"
     print(json.dumps({"bytes_per_linearisation": lin, "per_kernel": kern, "source": "ncu --set full capture " + path.split("/")[-1] +
-                      " (dram__bytes_read.sum + dram__bytes_write.sum, mean per launch of k_lin_lm2 + k_lin_cam2)"}, indent=1))
+                      " (dram__bytes_read.sum + dram__bytes_write.sum, mean per launch of " + what + ")"}, indent=1))
 
 
 if __name__ == "__main__":
