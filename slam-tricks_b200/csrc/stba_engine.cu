@@ -448,7 +448,16 @@ int Engine::build_pairs() {
   CK(cudaMemsetAsync(cnt, 0, std::max<int64_t>(n_blk, 1) * sizeof(int), stream));
   const uint8_t* lc = has_lm_const ? lm_const : nullptr;
   if (n_lm && n_blk) LAUNCH(this, (k_pair_pass<0>), grid_for(n_lm, 128), 128, n_lm, lm_ptr, obs_cam, free_of, lc, cnt, nullptr, nullptr, dup_flag);
-  LAUNCH(this, (k_exclusive_scan<int, int64_t>), 1, 1024, n_blk, cnt, blk_ptr);
+  if (n_blk > 4 * kScanTile) {
+    const int tiles = (int)((n_blk + kScanTile - 1) / kScanTile);
+    int64_t* tile_off = nullptr;
+    CKR(alloc(&tile_off, (size_t)tiles + 1));
+    LAUNCH(this, (k_scan_tile_sums<int, int64_t>), tiles, 1024, n_blk, cnt, tile_off);
+    LAUNCH(this, (k_exclusive_scan<int64_t, int64_t>), 1, 1024, (int64_t)tiles, tile_off, tile_off);
+    LAUNCH(this, (k_scan_tiles<int, int64_t>), tiles, 1024, n_blk, cnt, tile_off, blk_ptr);
+  } else {
+    LAUNCH(this, (k_exclusive_scan<int, int64_t>), 1, 1024, n_blk, cnt, blk_ptr);
+  }
   CK(cudaMemcpyAsync(&n_inc, blk_ptr + n_blk, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
   CK(cudaStreamSynchronize(stream));
   CKR(alloc(&inc, (size_t)n_inc));

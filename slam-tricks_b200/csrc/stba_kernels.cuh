@@ -581,6 +581,63 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(int64_t n, const TI* __
   if (threadIdx.x == 0) out[n] = carry;
 }
 
+// Multi-block exclusive scan for long inputs (the pair-block counts: ~500 k entries at C took 0.49 ms in the one-block
+// kernel above, 2 % of an end-to-end solve).  Three launches: per-block totals (kScanTile items per block), the
+// one-block scan over the totals, then every block scans its tile from its offset.  Integer: order-independent.
+constexpr int kScanItems = 8, kScanTile = 1024 * kScanItems;
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(int64_t n, const TI* __restrict__ in, TO* __restrict__ tile_sum) {
+  __shared__ TO warp_tot[32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  TO s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) s += base + k < n ? (TO)in[base + k] : (TO)0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    TO w = warp_tot[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = w;
+  }
+}
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(1024) k_scan_tiles(int64_t n, const TI* __restrict__ in, const TO* __restrict__ tile_off, TO* __restrict__ out) {
+  __shared__ TO warp_tot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+  TO x[kScanItems], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) { x[k] = base + k < n ? (TO)in[base + k] : (TO)0; s += x[k]; }
+  TO incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const TO y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    TO w = warp_tot[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const TO y = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += y;
+    }
+    warp_tot[lane] = w;
+  }
+  __syncthreads();
+  TO run = tile_off[blockIdx.x] + (warp ? warp_tot[warp - 1] : (TO)0) + incl - s;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += x[k];
+  }
+  if (base <= n - 1 && n - 1 < base + kScanItems) out[n] = run;      // the thread that owns the last item writes the total
+}
+
 // unstable bucket scatter; the per-bucket sort below makes the result the STABLE order
 __global__ void k_bucket_scatter(int64_t n, const int* __restrict__ key, const int* __restrict__ ptr,
                                  int* __restrict__ cursor, int* __restrict__ perm) {
