@@ -16,6 +16,7 @@
 // captured once per (S, n) into a CUDA graph.
 #include "stba_chol.cuh"
 
+#include <nccl.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -2560,6 +2561,38 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) k_chol_dag2(const Dag2Params P
   }
 }
 
+// ---- split factorisation (multi-GPU): the Schur-complement update of the trailing block ---------------------------
+// C(i, j) -= L(i, 0 : K) L(j, 0 : K)^T for a LIST of 128 x 128 tiles (i | j << 16) of the trailing matrix, K = the
+// width of the factored block-column range: the one embarrassingly parallel piece of a Cholesky factorisation, so the
+// piece that is spread over the GPUs (chol_factor_solve_split).  Persistent CTAs, tiles round-robin, upd_dev<4>.
+__global__ void __launch_bounds__(DAG_THREADS, 1) k_upd_list(double* __restrict__ S, int ld, int n_rows, int n, int K,
+                                                             const int* __restrict__ tiles, int n_list) {
+  extern __shared__ __align__(16) double sm[];
+  __shared__ unsigned long long s_cbar;
+  __shared__ long long s_prof[8];
+  unsigned cphase = 0;
+  if (threadIdx.x == 0) mbar_init(&s_cbar, 1);
+  __syncthreads();
+  for (int t = blockIdx.x; t < n_list; t += gridDim.x) {
+    const int e = __ldg(tiles + t);
+    upd_dev<4>(S, ld, n_rows, n, 0, K, (e & 0xffff) * NB, (e >> 16) * NB, sm, s_prof, &s_cbar, cphase);
+    __syncthreads();
+  }
+}
+// pack / unpack of trailing-matrix tiles (column-major 128 x 128 pieces of S, clipped to the n_rows x n matrix) into a
+// contiguous buffer, tile t at t * NB * NB: what one rank computed goes out to the others in one piece
+__global__ void k_tiles_pack(const double* __restrict__ S, int ld, int n_rows, int n, const int* __restrict__ tiles, int t0, double* __restrict__ buf, int unpack) {
+  const int e = __ldg(tiles + t0 + blockIdx.x), i0 = (e & 0xffff) * NB, j0 = (e >> 16) * NB;
+  double* b = buf + (size_t)(t0 + blockIdx.x) * NB * NB;
+  for (int x = threadIdx.x; x < NB * NB; x += blockDim.x) {
+    const int r = i0 + (x & (NB - 1)), c = j0 + (x >> 7);
+    if (r < n_rows && c < n) {
+      double* sp = const_cast<double*>(S) + (size_t)c * ld + r;
+      if (unpack) *sp = b[x]; else b[x] = *sp;
+    }
+  }
+}
+
 // The one-launch substitution kernels spin on flags of CTAs with a smaller block index.  CUDA does not promise
 // in-order dispatch once a grid exceeds the resident capacity, so the grid is cut into launches of at most one
 // CTA per SM: inside a launch every CTA is resident, across launches the producers have already finished.
@@ -3097,6 +3130,161 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
   }
 #endif
   if (n_launches) *n_launches += P->launches;
+  return STBA_OK;
+}
+
+// =================================================================================================
+// Split factorisation for N GPUs that hold the SAME matrix (the reduced camera system after the all-reduce).
+//   S = [A Bt; B C], A = the first m block columns.
+//   1. every rank: DAG factorisation restricted to the first m block columns, ALL rows (L_A, X = B L_A^-T, the
+//      right-hand-side row rides along) — k_chol_dag2 with T = m;
+//   2. the Schur complement C' = C - X X^T is a list of independent 128 x 128 x (128 m) tile updates: rank r
+//      computes tiles r, r + N, ... (k_upd_list), packs them, and the ranks exchange them (grouped ncclBroadcast);
+//   3. every rank: DAG factorisation of C' (a sub-matrix of S with the same leading dimension, the right-hand-side
+//      row still in row n), then ONE backward substitution over the whole factor.
+// The factorisation chain (one 128-column panel after the other, ~55 us each) stays replicated — it is a latency
+// chain, not work — the n^3/3-sized bulk between the two halves is what scales.  With one rank the same code runs
+// without the exchange (STBA_CHOL_SPLIT=1: tests).
+struct SplitPlan {
+  double* S = nullptr; double* rhs = nullptr; int* info = nullptr;
+  int n = 0, ld = 0, m = 0, T = 0, Tr = 0;
+  cudaStream_t stream = nullptr;
+  double *Linv = nullptr, *ybuf = nullptr, *pack = nullptr;
+  int* flags = nullptr;
+  int *tiles1 = nullptr, *tiles3 = nullptr, *dflags1 = nullptr, *dflags3 = nullptr, *upd_tiles = nullptr;
+  int n_tiles1 = 0, n_tiles3 = 0, units1 = 0, units3 = 0, n_upd = 0, grid = 0, W = 2, G = 8, D = 1;
+  size_t n_dflags1 = 0, n_dflags3 = 0;
+  int nranks = 1, rank = 0;
+  std::vector<int> first;       // first[r] .. first[r + 1]: tiles of rank r in upd_tiles
+};
+static void destroy_split(SplitPlan* p) {
+  if (!p) return;
+  cudaStream_t st = p->stream;
+  void* bufs[] = {p->Linv, p->ybuf, p->pack, p->flags, p->tiles1, p->tiles3, p->dflags1, p->dflags3, p->upd_tiles};
+  for (void* b : bufs) if (b) cudaFreeAsync(b, st);
+  delete p;
+}
+SplitWorkspace::~SplitWorkspace() { reset(); }
+void SplitWorkspace::reset() { destroy_split(plan); plan = nullptr; }
+
+// tile list + column starts + unit count of a DAG factorisation of `T` block columns over `Tr` tile rows (= build_dag2_plan)
+static int split_tables(int T, int Tr, int R64, int D, cudaStream_t stream, int** d_tiles, int* n_tiles, int* units_out, int** dflags, size_t* n_dflags) {
+  std::vector<int> tiles, col_start(T + 1, 0);
+  long long units = T;
+  for (int j = 0; j < T; ++j) {
+    col_start[j] = (int)tiles.size();
+    for (int i = j; i < Tr; ++i) {
+      tiles.push_back(i | (j << 16));
+      units += std::max(std::min(j, i - D) - ((D == 1 && i - j == 1) ? 1 : 0), 0);
+    }
+  }
+  col_start[T] = (int)tiles.size();
+  for (int h = 0; h < R64; ++h) units += std::max(0, std::min((h >> 1) - D, T));
+  *n_tiles = (int)tiles.size();
+  *units_out = (int)units;
+  std::vector<int> both(tiles);
+  both.insert(both.end(), col_start.begin(), col_start.end());
+  CKC(cudaMallocAsync((void**)d_tiles, both.size() * sizeof(int), stream));
+  CKC(cudaMemcpyAsync(*d_tiles, both.data(), both.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  CKC(cudaStreamSynchronize(stream));      // `both` is a local
+  *n_dflags = (size_t)F2_ARR + 4 * (size_t)T + 2 * Tr + R64 + 2 * (size_t)Tr * T;
+  CKC(cudaMallocAsync((void**)dflags, *n_dflags * sizeof(int), stream));
+  return STBA_OK;
+}
+
+static int split_launch_dag(const SplitPlan& P, double* S, int n, int T, double* Linv, int* dflags, size_t n_dflags, int* d_tiles, int n_tiles, int units) {
+  CKC(cudaMemsetAsync(dflags, 0, n_dflags * sizeof(int), P.stream));
+  Dag2Params dp;
+  dp.S = S; dp.ld = P.ld; dp.n = n; dp.n_rows = n + 1; dp.T = T; dp.Tr = (n + 1 + NB - 1) / NB; dp.R64 = (n + 1 + 63) / 64;
+  dp.Linv = Linv; dp.info = P.info; dp.flags = dflags;
+  dp.total_units = units; dp.W = P.W; dp.G = P.G; dp.D = P.D;
+  dp.tiles = d_tiles; dp.col_start = d_tiles + n_tiles; dp.n_tiles = n_tiles;
+  dp.prof = nullptr; dp.trace = nullptr;
+  void* args[] = {&dp};
+  CKC(cudaLaunchCooperativeKernel((const void*)k_chol_dag2, dim3(P.grid), dim3(DAG_THREADS), args, DAG_SMEM, P.stream));
+  return STBA_OK;
+}
+
+int chol_factor_solve_split(SplitWorkspace& ws, double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream, void* nccl_comm, int rank,
+                            int nranks, int* n_launches) {
+  if (n <= 0) return STBA_OK;
+  if (ld % 2 || ld < n + 1) return STBA_ERR_UNSUPPORTED;
+  const int T = (n + NB - 1) / NB, Tr = (n + 1 + NB - 1) / NB;
+  if (T < 8 || Tr > MAX_TR) return STBA_ERR_UNSUPPORTED;      // (callers fall back to chol_factor_solve)
+  SplitPlan* P = ws.plan;
+  if (!P || P->S != S || P->n != n || P->ld != ld || P->rhs != rhs || P->info != dev_info || P->nranks != nranks || P->rank != rank) {
+    destroy_split(P);
+    ws.plan = P = new SplitPlan();
+    P->S = S; P->n = n; P->ld = ld; P->rhs = rhs; P->info = dev_info; P->stream = stream; P->T = T; P->Tr = Tr; P->nranks = nranks; P->rank = rank;
+    P->m = T / 2 + 1;
+    if (const char* e = getenv("STBA_CHOL_SPLIT_M")) P->m = std::max(2, std::min(T - 2, atoi(e)));
+    int sms = 0, dev = 0;
+    CKC(cudaGetDevice(&dev));
+    CKC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    P->grid = sms;
+    if (P->grid < 4) return STBA_ERR_UNSUPPORTED;
+    CKC(cudaMallocAsync((void**)&P->Linv, (size_t)T * NB * NB * sizeof(double), stream));
+    CKC(cudaMemsetAsync(P->Linv, 0, (size_t)T * NB * NB * sizeof(double), stream));
+    CKC(cudaMallocAsync((void**)&P->ybuf, (size_t)T * NB * sizeof(double), stream));
+    CKC(cudaMallocAsync((void**)&P->flags, (size_t)T * sizeof(int), stream));
+    const int m = P->m, n3 = n - m * NB, T3 = (n3 + NB - 1) / NB, Tr3 = (n3 + 1 + NB - 1) / NB;
+    if (split_tables(m, Tr, (n + 1 + 63) / 64, P->D, stream, &P->tiles1, &P->n_tiles1, &P->units1, &P->dflags1, &P->n_dflags1) != STBA_OK) return STBA_ERR_CUDA;
+    if (split_tables(T3, Tr3, (n3 + 1 + 63) / 64, P->D, stream, &P->tiles3, &P->n_tiles3, &P->units3, &P->dflags3, &P->n_dflags3) != STBA_OK) return STBA_ERR_CUDA;
+    // trailing tiles, dealt round-robin in column-major order (every rank gets the same mix of near and far tiles);
+    // stored rank by rank so that each rank's tiles are one contiguous piece of the pack buffer
+    std::vector<std::vector<int>> mine(nranks);
+    int cnt = 0;
+    for (int j = m; j < T; ++j)
+      for (int i = j; i < Tr; ++i) mine[(cnt++) % nranks].push_back(i | (j << 16));
+    std::vector<int> all;
+    P->first.assign(nranks + 1, 0);
+    for (int r = 0; r < nranks; ++r) { P->first[r] = (int)all.size(); all.insert(all.end(), mine[r].begin(), mine[r].end()); }
+    P->first[nranks] = P->n_upd = (int)all.size();
+    CKC(cudaMallocAsync((void**)&P->upd_tiles, std::max<size_t>(all.size(), 1) * sizeof(int), stream));
+    CKC(cudaMemcpyAsync(P->upd_tiles, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CKC(cudaStreamSynchronize(stream));
+    if (nranks > 1) CKC(cudaMallocAsync((void**)&P->pack, (size_t)P->n_upd * NB * NB * sizeof(double), stream));
+    static bool attr_set = false;
+    if (!attr_set) {
+      CKC(cudaFuncSetAttribute(k_chol_dag2, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM));
+      CKC(cudaFuncSetAttribute(k_upd_list, cudaFuncAttributeMaxDynamicSharedMemorySize, DAG_SMEM));
+      CKC(cudaFuncSetAttribute(k_trsv_bwd_all, cudaFuncAttributeMaxDynamicSharedMemorySize, TBA_SMEM));
+      attr_set = true;
+    }
+  }
+  const int m = P->m, K = m * NB, n3 = n - K, T3 = (n3 + NB - 1) / NB;
+  // 1. first m block columns, all rows
+  k_put_row<<<(n + 255) / 256, 256, 0, stream>>>(S, ld, n, rhs);
+  if (split_launch_dag(*P, S, n, m, P->Linv, P->dflags1, P->n_dflags1, P->tiles1, P->n_tiles1, P->units1) != STBA_OK) return STBA_ERR_CUDA;
+  // 2. this rank's tiles of the Schur complement, then everybody's
+  const int t0 = P->first[rank], nt = P->first[rank + 1] - t0;
+  if (nt) k_upd_list<<<std::min(P->grid, nt), DAG_THREADS, DAG_SMEM, stream>>>(S, ld, n + 1, n, K, P->upd_tiles + t0, nt);
+  int launches = 3;
+  if (nranks > 1) {
+    if (nt) k_tiles_pack<<<nt, 256, 0, stream>>>(S, ld, n + 1, n, P->upd_tiles, t0, P->pack, 0);
+    ncclComm_t comm = static_cast<ncclComm_t>(nccl_comm);
+    if (ncclGroupStart() != ncclSuccess) return STBA_ERR_COMM;
+    for (int r = 0; r < nranks; ++r) {
+      const size_t cnt = (size_t)(P->first[r + 1] - P->first[r]) * NB * NB;
+      double* b = P->pack + (size_t)P->first[r] * NB * NB;
+      if (cnt && ncclBroadcast(b, b, cnt, ncclDouble, r, comm, stream) != ncclSuccess) return STBA_ERR_COMM;
+    }
+    if (ncclGroupEnd() != ncclSuccess) return STBA_ERR_COMM;
+    for (int r = 0; r < nranks; ++r) {
+      const int c = P->first[r + 1] - P->first[r];
+      if (r != rank && c) k_tiles_pack<<<c, 256, 0, stream>>>(S, ld, n + 1, n, P->upd_tiles, P->first[r], P->pack, 1);
+    }
+    launches += 1 + nranks;
+  }
+  // 3. the trailing block (same leading dimension, the right-hand-side row is still row n), then one backward substitution
+  double* S3 = S + (size_t)K * ld + K;
+  if (split_launch_dag(*P, S3, n3, T3, P->Linv + (size_t)m * NB * NB, P->dflags3, P->n_dflags3, P->tiles3, P->n_tiles3, P->units3) != STBA_OK) return STBA_ERR_CUDA;
+  k_get_row<<<(n + 255) / 256, 256, 0, stream>>>(S, ld, n, P->ybuf);
+  CKC(cudaMemsetAsync(rhs, 0xFF, (size_t)n * sizeof(double), stream));      // NaN = "not computed yet" (k_trsv_bwd_all, poll_data)
+  for (int b0 = 0; b0 < T; b0 += substitution_chunk())
+    k_trsv_bwd_all<<<std::min(T - b0, substitution_chunk()), TBA_THREADS, TBA_SMEM, stream>>>(S, ld, n, T, P->Linv, P->ybuf, rhs, P->flags, dev_info, b0, 1);
+  CKC(cudaGetLastError());
+  if (n_launches) *n_launches += launches + 3;
   return STBA_OK;
 }
 

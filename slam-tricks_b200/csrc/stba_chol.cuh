@@ -20,6 +20,19 @@ struct CholWorkspace {
 int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream,
                       int* n_launches);
 
+// Split factorisation for `nranks` GPUs holding the SAME matrix (multi-GPU reduced solve; see stba_chol.cu): first half of
+// the block columns on every rank, the Schur-complement update of the second half spread over the ranks (tiles exchanged
+// with NCCL broadcasts on `nccl_comm`, an ncclComm_t), second half and the backward substitution on every rank.  Returns
+// STBA_ERR_UNSUPPORTED for matrices too small to split (callers use chol_factor_solve).
+struct SplitPlan;
+struct SplitWorkspace {
+  SplitPlan* plan = nullptr;
+  ~SplitWorkspace();
+  void reset();
+};
+int chol_factor_solve_split(SplitWorkspace& ws, double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream, void* nccl_comm, int rank,
+                            int nranks, int* n_launches);
+
 // The two triangular solves on a finished lower Cholesky factor (column-major, leading dimension ld even) with the
 // one-launch flag-driven substitution kernels of the own back end; used behind cusolverDnDpotrf.
 struct SolvePlan;

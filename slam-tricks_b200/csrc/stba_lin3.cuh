@@ -91,7 +91,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
 // one landmark point (padded to 32 bytes: one sector) with ONE 256-bit load (sm_100: LDG.E.256) — a warp's 32 random
 // gathers cost 32 L1 wavefronts instead of the 64 of a 16-byte + an 8-byte load
 __device__ __forceinline__ void ldg_point(const double* p, double& x, double& y, double& z) {
-  double w;
+  [[maybe_unused]] double w;
   // (no L1 allocation: the points are used once per warp and would only evict each other; measured 41.0 -> 39.3 us at C)
   asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
   (void)w;

@@ -18,6 +18,8 @@ def _worker(rank, world, port, size, q, mode):
     import torch
     import torch.distributed as dist
     import stba
+    if size[0] >= 170:
+        os.environ["STBA_CHOL_SPLIT"] = "1"      # the opt-in split factorisation: Schur-complement tiles computed on different ranks
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
@@ -56,7 +58,11 @@ def _run(world, size, mode):
     return outs
 
 
-@pytest.mark.parametrize("world,size", [(2, (20, 300, 1200)), (2, (50, 5000, 50000)), (4, (50, 5000, 50000))])
+# (170 cameras: n = 1008 = 8 block columns, the smallest reduced system the opt-in split factorisation of the multi-GPU
+#  dense solve accepts — chol_factor_solve_split: Schur-complement tiles computed on different ranks and exchanged;
+#  the workers switch it on for this size)
+@pytest.mark.parametrize("world,size", [(2, (20, 300, 1200)), (2, (50, 5000, 50000)), (2, (170, 4000, 40000)), (4, (50, 5000, 50000)),
+                                        (4, (170, 4000, 40000))])
 def test_n_rank_solve_equals_single_gpu(stba, world, size):
     import torch
     if torch.cuda.device_count() < world:
