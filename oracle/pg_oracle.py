@@ -189,9 +189,12 @@ def spiral_truth(n, turns=10.0):
     return np.array([lie.rot_to_quat(Ri) for Ri in R]), pos
 
 
-def make_graph(n=200, offsets=(1, 2, 3, 4), sigma_t=0.01, sigma_r=0.005, drift_t=0.02, drift_r=0.01, seed=20221108):
+def make_graph(n=200, offsets=(1, 2, 3, 4), sigma_t=0.01, sigma_r=0.005, drift_t=0.02, drift_r=0.01, seed=20221108, closures=0,
+               closure_min=17):
     """Synthetic pose graph: truth = spiral, measurements = noisy relative poses on a band of offsets, initial guess =
-    odometry integration of noisier (i, i+1) steps (as the `obs` track of the reference's simulator drifts)."""
+    odometry integration of noisier (i, i+1) steps (as the `obs` track of the reference's simulator drifts).
+    `closures` extra edges (i, j), j - i >= closure_min, drawn after everything else (closures = 0 reproduces the
+    graphs of the earlier fixtures bit for bit): loop closures between poses far apart along the chain."""
     rng = np.random.default_rng(seed)
     qT, tT = spiral_truth(n)
     ei, ej = band_edges(n, offsets)
@@ -201,6 +204,12 @@ def make_graph(n=200, offsets=(1, 2, 3, 4), sigma_t=0.01, sigma_r=0.005, drift_t
     sq, st = measurements_from(qT, tT, np.arange(n - 1), np.arange(1, n), drift_t, drift_r, rng)
     for i in range(1, n):
         q0[i], t0[i] = compose(q0[i - 1], t0[i - 1], sq[i - 1], st[i - 1])
+    if closures:
+        ci = rng.integers(0, n - closure_min, closures)
+        cj = np.array([rng.integers(a + closure_min, n) for a in ci])
+        cq, ct = measurements_from(qT, tT, ci, cj, sigma_t, sigma_r, rng)
+        ei = np.concatenate([ei, ci.astype(np.int32)]); ej = np.concatenate([ej, cj.astype(np.int32)])
+        zq = np.concatenate([zq, cq]); zt = np.concatenate([zt, ct])
     return dict(q0=q0, t0=t0, ei=ei, ej=ej, zq=zq, zt=zt, q_truth=qT, t_truth=tT)
 
 

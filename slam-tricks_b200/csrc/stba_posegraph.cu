@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "../../include/stba.h"
+#include "stba_chol.cuh"
 
 namespace {
 
@@ -46,6 +47,7 @@ namespace {
   } while (0)
 
 constexpr int kMaxBand = 16;         // half-bandwidth in blocks the shared-memory ring is sized for
+constexpr int kMaxClosureBand = 8;   // widest band next to loop closures (the partitioned kernels need 2B - 1 <= 16)
 constexpr double kEps = 1e-10;       // Sophus epsilon (exp / log branches)
 constexpr double kSmall = 1e-5;      // series branch of the Jacobians (oracle/pg_oracle.py SMALL)
 
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(64)
 k_pg_linearize(int n, int B, const double* __restrict__ q, const double* __restrict__ t, const int* __restrict__ inc_ptr,
                const int* __restrict__ inc_edge, const int* __restrict__ ei, const int* __restrict__ ej,
                const double* __restrict__ zq, const double* __restrict__ zt, double* __restrict__ band, double* __restrict__ g,
-               double* __restrict__ cost_share) {
+               double* __restrict__ cost_share, const int* __restrict__ edge_cl, double* __restrict__ cl_blk) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   double* col = band + (size_t)c * (B + 1) * 36;
@@ -246,12 +248,14 @@ k_pg_linearize(int n, int B, const double* __restrict__ q, const double* __restr
       }
     }
     if (i == c) {                                  // block (j, c) = Jj^T Ji, owned by the lower-index endpoint
-      double* blk = col + (size_t)(j - c) * 36;
+      // inside the band: summed into the band column; a loop closure (j - c > B): its own 6 x 6 slot, written once
+      const bool far = j - c > B;
+      double* blk = far ? cl_blk + (size_t)edge_cl[e] * 36 : col + (size_t)(j - c) * 36;
       for (int a = 0; a < 6; ++a)
         for (int b = 0; b < 6; ++b) {
           double h = 0.0;
           for (int k = 0; k < 6; ++k) h += Jj[6 * k + a] * Ji[6 * k + b];
-          blk[6 * a + b] += h;
+          if (far) blk[6 * a + b] = h; else blk[6 * a + b] += h;
         }
     }
   }
@@ -758,6 +762,56 @@ k_pg_part_back(int B, int P, const int* __restrict__ pi0, const int* __restrict_
   cp_async_wait<0>();
 }
 
+// ---- loop closures: the reduced separator system as a DENSE matrix ---------------------------------------------
+// Edges longer than the band (|i - j| > B) couple poses that are far apart in the chain.  Their endpoints are put
+// into separator groups (B consecutive block columns, so that the interiors in between still never couple), the
+// interiors are eliminated exactly as above — any length, including empty — and the reduced system over the groups
+// receives (i) the band blocks among separator columns, (ii) the spike Gram blocks of the interiors, (iii) the
+// closure blocks.  It is no longer banded: it goes to the dense DAG Cholesky of the BA path (stba_chol.cu).
+// R: column-major, lower, leading dimension ld; reduced pose index of group g, slot sl = g B + sl.
+__global__ void __launch_bounds__(256)
+k_pg_cl_assemble(int B, int P, const int* __restrict__ pi0, const int* __restrict__ pi1, const double* __restrict__ A, const double* __restrict__ y,
+                 const double* __restrict__ G, double* __restrict__ R, int ld, double* __restrict__ yR) {
+  const int g = blockIdx.x;                             // group g: between interiors g and g + 1
+  const int CB = (B + 1) * 36, Rw = 1 + 12 * B, s0 = pi1[g];
+  const double* Gl = G + (size_t)g * Rw * Rw;           // interior g: this group is its RIGHT one  (columns 1 + 6B ..)
+  const double* Gr = G + (size_t)(g + 1) * Rw * Rw;     // interior g + 1: this group is its LEFT one (columns 1 ..)
+  const int oR = 1 + 6 * B, oL = 1;
+  for (int e = threadIdx.x; e < B * B * 36; e += 256) {
+    const int sl2 = e / (B * 36), sl1 = (e / 36) % B, a = (e % 36) / 6, k = e % 6;
+    if (sl2 < sl1 || (sl2 == sl1 && a < k)) continue;     // lower triangle only
+    const double v = A[(size_t)(s0 + sl1) * CB + (sl2 - sl1) * 36 + a * 6 + k]
+                     - Gl[(size_t)(oR + sl2 * 6 + a) * Rw + oR + sl1 * 6 + k] - Gr[(size_t)(oL + sl2 * 6 + a) * Rw + oL + sl1 * 6 + k];
+    R[(size_t)(6 * (g * B + sl1) + k) * ld + 6 * (g * B + sl2) + a] = v;
+  }
+  if (g > 0) {
+    // coupling with the previous group: through interior g (Gram) and, when that interior is shorter than B, directly
+    const int sp = pi1[g - 1];
+    for (int e = threadIdx.x; e < B * B * 36; e += 256) {
+      const int sl2 = e / (B * 36), sl1 = (e / 36) % B, a = (e % 36) / 6, k = e % 6;
+      const int c1 = sp + sl1, c2 = s0 + sl2;
+      double v = -Gl[(size_t)(oR + sl2 * 6 + a) * Rw + oL + sl1 * 6 + k];
+      if (c2 - c1 <= B) v += A[(size_t)c1 * CB + (c2 - c1) * 36 + a * 6 + k];
+      R[(size_t)(6 * ((g - 1) * B + sl1) + k) * ld + 6 * (g * B + sl2) + a] = v;
+    }
+  }
+  for (int e = threadIdx.x; e < 6 * B; e += 256)
+    yR[(size_t)g * 6 * B + e] = y[6 * (size_t)s0 + e] - Gl[(size_t)(oR + e) * Rw] - Gr[(size_t)(oL + e) * Rw];
+}
+// closure blocks (j, i), i < j: scaled like the band (A = S H S), added at the endpoints' reduced indices
+__global__ void __launch_bounds__(64)
+k_pg_cl_add(int n_cl, const int* __restrict__ cl_i, const int* __restrict__ cl_j, const int* __restrict__ sep_of, const double* __restrict__ cl_blk,
+            const double* __restrict__ scale, double* __restrict__ R, int ld) {
+  const int e = blockIdx.x, t = threadIdx.x;
+  if (e >= n_cl || t >= 36) return;
+  const int i = cl_i[e], j = cl_j[e], a = t / 6, k = t % 6;
+  if (i == 0) return;                                   // the constant pose has no column
+  const int ri = sep_of[i], rj = sep_of[j];
+  const double v = scale[6 * j + a] * cl_blk[(size_t)e * 36 + t] * scale[6 * i + k];
+  atomicAdd(R + (size_t)(6 * ri + k) * ld + 6 * rj + a, v);      // (several closures may join the same pair of poses)
+}
+__global__ void k_pg_or_info(int* info, const int* other) { if (*other != 0 && *info == 0) *info = *other > 0 ? *other : 1; }
+
 // step: delta = -ys * scale, candidate T+ = T Exp(delta); per-pose shares of |step|^2, |x+|... and of the model cost change
 __global__ void k_pg_update(int n, const double* __restrict__ q, const double* __restrict__ t, const double* __restrict__ ys,
                             const double* __restrict__ scale, const double* __restrict__ gs, const double* __restrict__ diag,
@@ -848,6 +902,12 @@ struct stba_pg {
   int P = 1, Br = 1;
   int *pi0 = nullptr, *pi1 = nullptr;
   double *Z = nullptr, *G = nullptr, *Rb = nullptr, *yR = nullptr;
+  // loop closures (edges longer than the band): endpoints live in separator groups, the reduced system is dense
+  bool closure = false;
+  int n_cl = 0, n_red = 0, ld_red = 0;
+  int *edge_cl = nullptr, *cl_i = nullptr, *cl_j = nullptr, *sep_of = nullptr, *info2 = nullptr;
+  double *cl_blk = nullptr, *R = nullptr;
+  stba::CholWorkspace chol;
   std::vector<void*> allocs;
   template <typename T>
   int alloc(T** p, size_t count) {
@@ -858,6 +918,8 @@ struct stba_pg {
     return STBA_OK;
   }
   ~stba_pg() {
+    chol.reset();
+    if (s) cudaStreamSynchronize(s);
     for (void* p : allocs) cudaFree(p);
     if (red_host) cudaFreeHost(red_host);
     if (s) cudaStreamDestroy(s);
@@ -878,6 +940,19 @@ struct stba_pg {
     k_pg_part_rhs<<<P, 256, 0, s>>>(B, P, pi0, pi1, A, ys, Z);
     k_pg_part_factor<<<P, BS_THREADS, factor_smem(), s>>>(B, pi0, pi1, A, Z, info);
     k_pg_part_gram<<<P, 256, 32 * Rw * (int)sizeof(double), s>>>(B, pi0, pi1, Z, G);
+    if (closure) {
+      CK(cudaMemsetAsync(R, 0, (size_t)ld_red * n_red * sizeof(double), s));
+      CK(cudaMemsetAsync(info2, 0, sizeof(int), s));
+      k_pg_cl_assemble<<<P - 1, 256, 0, s>>>(B, P, pi0, pi1, A, ys, G, R, ld_red, yR);
+      if (n_cl) k_pg_cl_add<<<n_cl, 64, 0, s>>>(n_cl, cl_i, cl_j, sep_of, cl_blk, scale, R, ld_red);
+      int nl = 0;
+      const int r = stba::chol_factor_solve(chol, R, n_red, ld_red, yR, info2, s, &nl);
+      if (r != STBA_OK) return r;
+      k_pg_or_info<<<1, 1, 0, s>>>(info, info2);
+      k_pg_part_back<<<P, BS_THREADS, back_smem(), s>>>(B, P, pi0, pi1, A, Z, yR, ys);
+      launches += 7 + nl;
+      return STBA_OK;
+    }
     CK(cudaMemsetAsync(Rb, 0, (size_t)(P - 1) * B * (Br + 1) * 36 * sizeof(double), s));
     k_pg_part_assemble<<<P - 1, 256, 0, s>>>(B, P, pi1, A, ys, G, Rb, yR);
     k_pg_band_solve<<<1, BS_THREADS, band_smem(Br), s>>>((P - 1) * B, Br, Rb, yR, info);
@@ -887,7 +962,7 @@ struct stba_pg {
   }
 
   int linearize(double* cost) {
-    k_pg_linearize<<<(n + 63) / 64, 64, 0, s>>>(n, B, q, t, inc_ptr, inc_edge, ei, ej, zq, zt, band, g, share);
+    k_pg_linearize<<<(n + 63) / 64, 64, 0, s>>>(n, B, q, t, inc_ptr, inc_edge, ei, ej, zq, zt, band, g, share, edge_cl, cl_blk);
     k_pg_sum<<<1, 256, 0, s>>>(n, 1, 1, share, red);
     launches += 2;
     CK(cudaMemcpyAsync(red_host, red, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -918,14 +993,27 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
     if (ei[e] < 0 || ej[e] >= n_poses || ei[e] >= ej[e]) return STBA_ERR_INVALID_ARGUMENT;     // i < j
     B = std::max(B, ej[e] - ei[e]);
   }
-  if (B > kMaxBand) return STBA_ERR_UNSUPPORTED;       // long-range loop closures need a general sparse solver
+  // Loop closures: edges longer than the band.  The band is the largest offset <= 8 that at least 1 % of the poses use
+  // (the odometry / local-window edges); every longer edge is a closure whose endpoints become separator columns of
+  // the partitioned solve, and the reduced system is solved densely (k_pg_cl_*).
+  bool closure = false;
+  if (B > kMaxBand || getenv("STBA_PG_CLOSURE_BAND")) {
+    std::vector<int64_t> hist(kMaxClosureBand + 1, 0);
+    for (int64_t e = 0; e < n_edges; ++e) if (ej[e] - ei[e] <= kMaxClosureBand) ++hist[ej[e] - ei[e]];
+    int Bc = 1;
+    for (int d = 1; d <= kMaxClosureBand; ++d) if (hist[d] >= std::max<int64_t>(1, n_poses / 100)) Bc = d;
+    if (const char* ov = getenv("STBA_PG_CLOSURE_BAND")) Bc = std::max(1, std::min(kMaxClosureBand, atoi(ov)));     // tests
+    closure = B > Bc;
+    if (closure) B = Bc;
+    if (B > kMaxBand) return STBA_ERR_UNSUPPORTED;
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STBA_ERR_NO_DEVICE; }
   if (device < 0 || device >= ndev) return STBA_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(device));
   stba_pg* h = new (std::nothrow) stba_pg();
   if (!h) return STBA_ERR_CUDA;
-  h->device = device; h->n = n_poses; h->m = n_edges; h->B = B;
+  h->device = device; h->n = n_poses; h->m = n_edges; h->B = B; h->closure = closure;
   // pose -> incident edges (host index logic; edges in their given order: the summation order of the gather)
   std::vector<int> ptr((size_t)n_poses + 1, 0), inc(2 * (size_t)n_edges);
   for (int64_t e = 0; e < n_edges; ++e) { ++ptr[ei[e] + 1]; ++ptr[ej[e] + 1]; }
@@ -938,7 +1026,8 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
 #define CKH(x) do { int r_ = (x); if (r_ != STBA_OK) return fail(r_); } while (0)
 #define CKD(x) do { if ((x) != cudaSuccess) return fail(STBA_ERR_CUDA); } while (0)
   CKD(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
-  const size_t N = n_poses, M = std::max<int64_t>(n_edges, 1), CBn = (size_t)(B + 1) * 36;
+  // (with loop closures the last separator group may reach past the last pose: B dummy identity columns behind it)
+  const size_t N = (size_t)n_poses + (closure ? B : 0), M = std::max<int64_t>(n_edges, 1), CBn = (size_t)(B + 1) * 36;
   CKH(h->alloc(&h->q, 4 * N)); CKH(h->alloc(&h->t, 3 * N)); CKH(h->alloc(&h->q2, 4 * N)); CKH(h->alloc(&h->t2, 3 * N));
   CKH(h->alloc(&h->zq, 4 * M)); CKH(h->alloc(&h->zt, 3 * M)); CKH(h->alloc(&h->ei, M)); CKH(h->alloc(&h->ej, M));
   CKH(h->alloc(&h->inc_ptr, N + 1)); CKH(h->alloc(&h->inc_edge, 2 * M)); CKH(h->alloc(&h->info, 1));
@@ -951,8 +1040,8 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
   CKD(cudaMemsetAsync(h->gs, 0, 6 * N * sizeof(double), h->s));
   CKD(cudaMemsetAsync(h->diag, 0, 6 * N * sizeof(double), h->s));
   CKD(cudaMemsetAsync(h->scale, 0, 6 * N * sizeof(double), h->s));
-  CKD(cudaMemcpyAsync(h->q, q, 4 * N * sizeof(double), cudaMemcpyHostToDevice, h->s));
-  CKD(cudaMemcpyAsync(h->t, t, 3 * N * sizeof(double), cudaMemcpyHostToDevice, h->s));
+  CKD(cudaMemcpyAsync(h->q, q, 4 * (size_t)n_poses * sizeof(double), cudaMemcpyHostToDevice, h->s));
+  CKD(cudaMemcpyAsync(h->t, t, 3 * (size_t)n_poses * sizeof(double), cudaMemcpyHostToDevice, h->s));
   if (n_edges) {
     CKD(cudaMemcpyAsync(h->zq, zq, 4 * (size_t)n_edges * sizeof(double), cudaMemcpyHostToDevice, h->s));
     CKD(cudaMemcpyAsync(h->zt, zt, 3 * (size_t)n_edges * sizeof(double), cudaMemcpyHostToDevice, h->s));
@@ -961,6 +1050,63 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
     CKD(cudaMemcpyAsync(h->inc_edge, inc.data(), inc.size() * sizeof(int), cudaMemcpyHostToDevice, h->s));
   }
   CKD(cudaMemcpyAsync(h->inc_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice, h->s));
+  if (closure) {
+    // ---- loop closures: separator groups at the closure endpoints (and every L columns), interiors of any length ----
+    std::vector<int> h_edge_cl((size_t)M, -1), h_cl_i, h_cl_j;
+    std::vector<uint8_t> mand((size_t)n_poses, 0);
+    for (int64_t e = 0; e < n_edges; ++e)
+      if (ej[e] - ei[e] > B) {
+        h_edge_cl[e] = (int)h_cl_i.size();
+        h_cl_i.push_back(ei[e]); h_cl_j.push_back(ej[e]);
+        mand[ei[e]] = 1; mand[ej[e]] = 1;
+      }
+    h->n_cl = (int)h_cl_i.size();
+    const int L = std::max(std::max(B, 8), (int)std::lround(std::sqrt((double)n_poses * B)));      // interior length without closures nearby
+    std::vector<int> i0, i1, sep((size_t)N, -1);
+    int cur = 0, next_m = 0;
+    for (;;) {
+      while (next_m < n_poses && (next_m < cur || !mand[next_m])) ++next_m;      // first closure endpoint at or after cur
+      const int cut = std::min(next_m, cur + L);
+      if (cut >= n_poses) { i0.push_back(cur); i1.push_back(std::max(cur, n_poses)); break; }
+      i0.push_back(cur); i1.push_back(cut);
+      const int g = (int)i1.size() - 1;
+      for (int sl = 0; sl < B; ++sl) sep[cut + sl] = g * B + sl;
+      cur = cut + B;
+      if (cur >= n_poses) { i0.push_back(cur); i1.push_back(cur); break; }
+    }
+    // (a final interior that starts inside the padding is empty by construction; one that ends at n_poses is real)
+    if (i1.back() > n_poses) i1.back() = i0.back();
+    const int P = (int)i0.size();
+    h->P = P; h->Br = 1;
+    h->n_red = 6 * B * (P - 1);
+    h->ld_red = h->n_red + 2;
+    const size_t Rw = 1 + 12 * (size_t)B;
+    CKH(h->alloc(&h->pi0, P)); CKH(h->alloc(&h->pi1, P));
+    CKH(h->alloc(&h->Z, N * 6 * Rw)); CKH(h->alloc(&h->G, (size_t)P * Rw * Rw));
+    CKH(h->alloc(&h->yR, (size_t)std::max(h->n_red, 1)));
+    CKH(h->alloc(&h->R, (size_t)h->ld_red * std::max(h->n_red, 1)));
+    CKH(h->alloc(&h->edge_cl, M)); CKH(h->alloc(&h->cl_i, std::max(h->n_cl, 1))); CKH(h->alloc(&h->cl_j, std::max(h->n_cl, 1)));
+    CKH(h->alloc(&h->cl_blk, 36 * (size_t)std::max(h->n_cl, 1))); CKH(h->alloc(&h->sep_of, N)); CKH(h->alloc(&h->info2, 1));
+    CKD(cudaMemsetAsync(h->cl_blk, 0, 36 * (size_t)std::max(h->n_cl, 1) * sizeof(double), h->s));
+    CKD(cudaMemsetAsync(h->Z, 0, N * 6 * Rw * sizeof(double), h->s));
+    CKD(cudaMemcpyAsync(h->pi0, i0.data(), P * sizeof(int), cudaMemcpyHostToDevice, h->s));
+    CKD(cudaMemcpyAsync(h->pi1, i1.data(), P * sizeof(int), cudaMemcpyHostToDevice, h->s));
+    CKD(cudaMemcpyAsync(h->edge_cl, h_edge_cl.data(), (size_t)M * sizeof(int), cudaMemcpyHostToDevice, h->s));
+    CKD(cudaMemcpyAsync(h->cl_i, h_cl_i.data(), h_cl_i.size() * sizeof(int), cudaMemcpyHostToDevice, h->s));
+    CKD(cudaMemcpyAsync(h->cl_j, h_cl_j.data(), h_cl_j.size() * sizeof(int), cudaMemcpyHostToDevice, h->s));
+    CKD(cudaMemcpyAsync(h->sep_of, sep.data(), N * sizeof(int), cudaMemcpyHostToDevice, h->s));
+    // the dummy columns behind the last pose: identity diagonal blocks, no coupling, zero right-hand side
+    {
+      std::vector<double> pad((size_t)B * CBn, 0.0);
+      for (int c = 0; c < B; ++c) for (int k = 0; k < 6; ++k) pad[(size_t)c * CBn + 7 * k] = 1.0;
+      CKD(cudaMemcpyAsync(h->A + (size_t)n_poses * CBn, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice, h->s));
+      CKD(cudaMemcpyAsync(h->band + (size_t)n_poses * CBn, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice, h->s));
+      CKD(cudaStreamSynchronize(h->s));       // host vectors above are locals
+    }
+    CKD(cudaFuncSetAttribute(k_pg_part_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, h->factor_smem()));
+    CKD(cudaFuncSetAttribute(k_pg_part_back, cudaFuncAttributeMaxDynamicSharedMemorySize, h->back_smem()));
+    CKD(cudaFuncSetAttribute(k_pg_part_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * (int)Rw * (int)sizeof(double)));
+  } else
   {
     // partitions: serial depth N / P + P B is smallest near P = sqrt(N / B); every interior must be at least B
     // columns long (so that interiors never couple) and the reduced half-bandwidth 2B - 1 must fit the ring
@@ -1051,7 +1197,7 @@ int stba_pg_time_linearize(stba_pg* pg, int reps, float* ms) {
   for (int r = 0; r < reps; ++r) {
     CK(cudaEventRecord(a, pg->s));
     k_pg_linearize<<<(pg->n + 63) / 64, 64, 0, pg->s>>>(pg->n, pg->B, pg->q, pg->t, pg->inc_ptr, pg->inc_edge, pg->ei, pg->ej, pg->zq, pg->zt, pg->band,
-                                                     pg->g, pg->share);
+                                                     pg->g, pg->share, pg->edge_cl, pg->cl_blk);
     CK(cudaEventRecord(b, pg->s));
     CK(cudaStreamSynchronize(pg->s));
     CK(cudaEventElapsedTime(&ms[r], a, b));

@@ -164,6 +164,39 @@ def test_partitioned_band_solve_is_the_same_solver(stba, monkeypatch, n, offsets
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,offsets,closures,band", [(400, (1, 2, 3, 4), 12, None), (300, (1,), 25, None), (500, (1, 2), 1, None), (260, (1, 3), 40, None),
+                                                     (200, (1, 2, 3, 4), 0, 2)])
+def test_loop_closures_match_oracle(stba, monkeypatch, n, offsets, closures, band):
+    """Edges longer than the band (|i - j| > 16): their endpoints become separator groups of the partitioned solve and the
+    reduced system is solved densely — an exact elimination, so the LM iterates must reproduce the oracle (which solves
+    the full sparse normal equations): same iterations, same accept / reject sequence, same poses.  Closures that share
+    endpoints, closures at pose 0 (constant) and at the last pose, a single closure, and (last case) band edges forced
+    into the closure set are covered by the seeds below."""
+    if band is not None:
+        monkeypatch.setenv("STBA_PG_CLOSURE_BAND", str(band))
+    G = pg.make_graph(n, offsets=offsets, closures=closures)
+    if closures >= 12:          # make sure the corner cases are in: pose 0, the last pose, a repeated pair
+        G["ei"][-1], G["ej"][-1] = 0, n - 1
+        G["ei"][-2], G["ej"][-2] = G["ei"][-3], G["ej"][-3]
+        G["zq"][-1:], G["zt"][-1:] = pg.measurements_from(G["q_truth"], G["t_truth"], G["ei"][-1:], G["ej"][-1:])
+        G["zq"][-2:-1], G["zt"][-2:-1] = pg.measurements_from(G["q_truth"], G["t_truth"], G["ei"][-2:-1], G["ej"][-2:-1])
+    want_q, want_t, want = pg.solve(G["q0"], G["t0"], G["ei"], G["ej"], G["zq"], G["zt"])
+    with stba.posegraph.PoseGraph(G["q0"], G["t0"], G["ei"], G["ej"], G["zq"], G["zt"]) as p:
+        cost, g, H, bw = p.linearize()
+        s = p.solve()
+        q, t = p.get_state()
+    want_cost, want_g, want_H = _dense_blocks(G)
+    assert bw == (band if band is not None else max(offsets))
+    assert abs(cost - want_cost) <= 1e-12 * want_cost and np.allclose(g, want_g, rtol=1e-10, atol=1e-12) and np.allclose(H, want_H, rtol=1e-10, atol=1e-12)
+    assert s.termination_type == want.termination_type and s.message == want.message
+    assert len(s.iterations) == len(want.iterations)
+    assert [i["step_is_successful"] for i in s.iterations] == [int(i["step_is_successful"]) for i in want.iterations]
+    assert np.allclose([i["cost"] for i in s.iterations], [i["cost"] for i in want.iterations], rtol=1e-8)
+    assert abs(np.sqrt(2 * s.final_cost) - np.sqrt(2 * want.final_cost)) <= 1e-6 * np.sqrt(2 * want.final_cost)
+    assert np.max(np.abs(q - want_q)) < 1e-7 and np.max(np.abs(t - want_t)) < 1e-7
+
+
+@pytest.mark.gpu
 def test_reference_track_fixture(stba, st4):
     with stba.posegraph.PoseGraph(st4["q0"], st4["t0"], st4["ei"], st4["ej"], st4["zq"], st4["zt"]) as p:
         s = p.solve()
@@ -191,17 +224,37 @@ def test_options_rejections_and_edge_cases(stba):
         s = p.solve(opt)
     assert np.allclose([i["cost"] for i in s.iterations], [i["cost"] for i in want.iterations], rtol=1e-8)
     assert np.allclose([i["trust_region_radius"] for i in s.iterations], [i["trust_region_radius"] for i in want.iterations], rtol=1e-6)
-    # bandwidth beyond the ring, reversed edges
+    # offsets beyond the ring (round 1: STBA_ERR_UNSUPPORTED) are loop closures now: every pose is an endpoint here
     far = pg.make_graph(40, offsets=(1, 17))
-    with pytest.raises(stba.capi.StbaError) as e:
-        stba.posegraph.PoseGraph(far["q0"], far["t0"], far["ei"], far["ej"], far["zq"], far["zt"])
-    assert e.value.status == 4       # STBA_ERR_UNSUPPORTED
+    want_q, want_t, want = pg.solve(far["q0"], far["t0"], far["ei"], far["ej"], far["zq"], far["zt"])
+    with stba.posegraph.PoseGraph(far["q0"], far["t0"], far["ei"], far["ej"], far["zq"], far["zt"]) as p:
+        s = p.solve()
+        q, t = p.get_state()
+    assert len(s.iterations) == len(want.iterations) and np.max(np.abs(q - want_q)) < 1e-7 and np.max(np.abs(t - want_t)) < 1e-7
+    # reversed edges
     with pytest.raises(stba.capi.StbaError):
         stba.posegraph.PoseGraph(G["q0"], G["t0"], G["ej"], G["ei"], G["zq"], G["zt"])
     # a single pose without edges is already solved
     with stba.posegraph.PoseGraph(G["q0"][:1], G["t0"][:1], [], [], np.zeros((0, 4)), np.zeros((0, 3))) as p:
         s = p.solve()
     assert s.termination_type == "CONVERGENCE" and s.final_cost == 0.0
+
+
+@pytest.mark.gpu
+def test_config_10k_poses_with_one_percent_loop_closures(stba):
+    """BASELINE configs[4] size with 100 long-range closures (1 % of the poses) on top of the 39 990 band edges: the
+    oracle's sparse LM (seconds) against the GPU path with closure endpoints as separators and a dense reduced solve."""
+    G = pg.make_graph(10000, closures=100)
+    want_q, want_t, want = pg.solve(G["q0"], G["t0"], G["ei"], G["ej"], G["zq"], G["zt"])
+    with stba.posegraph.PoseGraph(G["q0"], G["t0"], G["ei"], G["ej"], G["zq"], G["zt"]) as p:
+        s = p.solve()
+        q, t = p.get_state()
+    assert s.termination_type == want.termination_type and len(s.iterations) == len(want.iterations)
+    assert [i["step_is_successful"] for i in s.iterations] == [int(i["step_is_successful"]) for i in want.iterations]
+    assert np.allclose([i["cost"] for i in s.iterations], [i["cost"] for i in want.iterations], rtol=1e-8)
+    assert abs(np.sqrt(2 * s.final_cost) - np.sqrt(2 * want.final_cost)) <= 1e-6 * np.sqrt(2 * want.final_cost)
+    assert np.max(np.abs(q - want_q)) < 1e-6 and np.max(np.abs(t - want_t)) < 1e-6
+    print("10k poses + 100 closures: %d iterations, %.1f ms, %d launches" % (len(s.iterations), s.total_time_ms, s.gpu_launches))
 
 
 @pytest.mark.gpu
