@@ -551,12 +551,31 @@ def run_pg(args):
             cpu = {"value": n_it / dt, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": "1 full LM solve of the same graph (%d iterations, %.1f s) with oracle/pg_oracle.py (NumPy + SciPy sparse)" % (n_it, dt),
                    "note": "the reference has no pose-graph solver (SURVEY.md §8d): the oracle is the specification"}
+        # the same graph with 1 % loop closures (100 edges between poses far apart along the chain): closure endpoints
+        # become separators of the partitioned solve, the reduced system goes to the dense DAG Cholesky
+        closures = None
+        if world == 1:
+            Gc = stba.synth.pose_graph(PG_N, offsets=PG_OFFSETS, closures=PG_N // 100)
+            with stba.posegraph.PoseGraph(Gc["q0"], Gc["t0"], Gc["ei"], Gc["ej"], Gc["zq"], Gc["zt"], device=local) as pc:
+                pc.save_state()
+                for _ in range(2):
+                    pc.restore_state(); sc = pc.solve()
+                torch.cuda.synchronize()
+                tc = time.perf_counter()
+                itc = 0
+                for _ in range(5):
+                    pc.restore_state(); sc = pc.solve(); itc += n_iters(sc)
+                torch.cuda.synchronize()
+                tc = time.perf_counter() - tc
+            closures = {"edges": int(len(Gc["ei"])), "loop_closures": PG_N // 100, "value": itc / tc, "unit": UNIT, "ms_per_solve": 1e3 * tc / 5,
+                        "iterations_per_solve": n_iters(sc), "termination": sc.termination_type, "final_cost": sc.final_cost}
         line = {"metric": METRIC_PG, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": {"workload": workload_string("PG")},
                 "details": {"step": "one full LM solve from the drifted odometry initial guess", "parallelism": "replicas only (x%d)" % world if world > 1 else "single GPU"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "iterations_per_solve": n_iters(last), "termination": last.termination_type, "final_cost": last.final_cost}
+                "iterations_per_solve": n_iters(last), "termination": last.termination_type, "final_cost": last.final_cost,
+                "with_loop_closures": closures}
         print(json.dumps(line))
     pgr.close()
     if world > 1:

@@ -309,8 +309,10 @@ int stba_calib_optimize_timed(int device, int32_t n_views, const int32_t* view_p
 /* Jacobians its SE(3) notes (st23-lie-group-v2/doc.tex:862-997); oracle/pg_oracle.py is the */
 /* specification.  Poses q f64[n,4] xyzw + t f64[n,3] (body -> world); edge e = (ei < ej,    */
 /* measured T_i^-1 T_j as zq f64[m,4], zt f64[m,3]); residual Log(Z^-1 T_i^-1 T_j) in Sophus */
-/* order [rho, theta]; manifold T <- T Exp(delta); pose 0 constant.  J^T J is block-banded:  */
-/* max(ej - ei) <= 16 blocks is supported (STBA_ERR_UNSUPPORTED beyond).                    */
+/* order [rho, theta]; manifold T <- T Exp(delta); pose 0 constant.  J^T J is block-banded   */
+/* (half-bandwidth = max(ej - ei) <= 16 blocks) plus loop closures: edges longer than that   */
+/* are eliminated exactly through separator groups at their endpoints and a dense reduced    */
+/* solve (band next to closures: the largest offset <= 8 used by >= 1 % of the poses).       */
 /* ==================================================================================== */
 typedef struct stba_pg stba_pg;
 int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, const double* q,

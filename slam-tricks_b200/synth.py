@@ -350,9 +350,11 @@ def _relative(q, t, ei, ej):
     return _se3_compose(qi, ti, q[ej], t[ej])
 
 
-def pose_graph(n=200, offsets=(1, 2, 3, 4), sigma_t=0.01, sigma_r=0.005, drift_t=0.02, drift_r=0.01, seed=20221108, turns=10.0):
+def pose_graph(n=200, offsets=(1, 2, 3, 4), sigma_t=0.01, sigma_r=0.005, drift_t=0.02, drift_r=0.01, seed=20221108, turns=10.0, closures=0,
+               closure_min=17):
     """Returns dict(q0, t0, ei, ej, zq, zt, q_truth, t_truth): truth = spiral, measurements = noisy relative poses on
-    a band of index offsets (edges sorted by (i, j)), initial guess = integration of noisier (i, i+1) steps."""
+    a band of index offsets (edges sorted by (i, j)), initial guess = integration of noisier (i, i+1) steps; `closures`
+    extra edges (i, j) with j - i >= closure_min appended behind the band edges (loop closures)."""
     rng = np.random.default_rng(seed)
     s = np.arange(n) / max(n - 1, 1)
     z = 2.0 * s
@@ -382,6 +384,12 @@ def pose_graph(n=200, offsets=(1, 2, 3, 4), sigma_t=0.01, sigma_r=0.005, drift_t
     q0[0], t0[0] = qT[0], tT[0]
     for i in range(1, n):
         q0[i], t0[i] = _se3_compose(q0[i - 1], t0[i - 1], sq[i - 1], st[i - 1])
+    if closures:
+        ci = rng.integers(0, n - closure_min, closures)
+        cj = np.array([rng.integers(a + closure_min, n) for a in ci])
+        cq, ct = measure(ci, cj, sigma_t, sigma_r)
+        ei = np.concatenate([ei, ci.astype(np.int32)]); ej = np.concatenate([ej, cj.astype(np.int32)])
+        zq = np.concatenate([zq, cq]); zt = np.concatenate([zt, ct])
     return dict(q0=q0, t0=t0, ei=ei, ej=ej, zq=zq, zt=zt, q_truth=qT, t_truth=tT)
 
 

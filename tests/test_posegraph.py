@@ -79,8 +79,8 @@ def test_oracle_reduces_the_drift_of_the_reference_track(st4):
 
 def test_product_side_generator_equals_the_oracles(stba):
     # slam-tricks_b200/synth.py pose_graph is self-contained (product code never imports oracle/) and bit-identical
-    for n, off in ((120, (1, 2, 3, 4)), (90, (1, 7, 16))):
-        a, b = stba.synth.pose_graph(n, offsets=off), pg.make_graph(n, offsets=off)
+    for n, off, cl in ((120, (1, 2, 3, 4), 0), (90, (1, 7, 16), 0), (150, (1, 2), 9)):
+        a, b = stba.synth.pose_graph(n, offsets=off, closures=cl), pg.make_graph(n, offsets=off, closures=cl)
         assert all(np.array_equal(a[k], b[k]) for k in b)
 
 
