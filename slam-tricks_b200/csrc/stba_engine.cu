@@ -432,7 +432,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
 
   // ---- Schur / dense workspaces ----
   if (!linearize_only) {
-    CKR(alloc(&E, 18 * (size_t)nobs));
+    CKR(alloc(&E, kEStride * (size_t)nobs));
     CKR(alloc(&S, (size_t)ld * n)); CKR(alloc(&rhs, (size_t)n));
     CK(cudaMemsetAsync(S, 0, std::max<size_t>((size_t)ld * n, 1) * sizeof(double), stream));
   }

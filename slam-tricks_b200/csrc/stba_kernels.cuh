@@ -12,6 +12,18 @@ namespace stba {
 constexpr int kBlock = 128;          // threads per CTA of the per-landmark / per-chunk kernels
 constexpr int kCamAcc = 23;          // camera-frame accumulators of lin_cam (see below)
 constexpr int kDiagAcc = 27;         // 21 (E E^T upper) + 6 (E h) of schur_diag
+// E record per observation: 18 doubles padded to 20 (160 B = five 32-byte sectors).  The consumers gather whole records
+// at random (k_schur_off: two per pair, one thread per block) and are bound by L1 wavefronts, one per lane and load
+// instruction: five 256-bit loads (sm_100 LDG.E.256) per record instead of nine 128-bit ones.
+constexpr int kEStride = 20;
+__device__ __forceinline__ void ldg_e(const double* __restrict__ rec, double (&e)[20]) {
+#pragma unroll
+  for (int k = 0; k < 20; k += 4)
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(e[k]), "=d"(e[k + 1]), "=d"(e[k + 2]), "=d"(e[k + 3]) : "l"(rec + k));
+}
+__device__ __forceinline__ void stg4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // camera tiles: q,t -> [R row-major | t]
@@ -127,10 +139,10 @@ k_schur_E(int64_t n_obs, const int* __restrict__ obs_cam, const int* __restrict_
           const uint8_t* __restrict__ lm_const, const double* __restrict__ Linv, double* __restrict__ E) {
   for (int64_t o = blockIdx.x * (int64_t)kBlock + threadIdx.x; o < n_obs; o += (int64_t)gridDim.x * kBlock) {
     const int c = __ldg(obs_cam + o), l = __ldg(obs_lm + o);
-    double2* Eo = reinterpret_cast<double2*>(E + 18 * (size_t)o);
+    double* Eo = E + kEStride * (size_t)o;
     if (cam_const[c] || (lm_const && lm_const[l])) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k) Eo[k] = make_double2(0.0, 0.0);
+      for (int k = 0; k < kEStride; k += 4) stg4(Eo + k, 0.0, 0.0, 0.0, 0.0);
       continue;
     }
     const double2 uv = ldg2(obs_uv + 2 * (size_t)o);
@@ -151,7 +163,8 @@ k_schur_E(int64_t n_obs, const int* __restrict__ obs_cam, const int* __restrict_
     // Z = Jl Linv^T  (2x3):  Z[r][k] = sum_{j<=k} Jl[r][j] Linv[k][j]
     const double z00 = J0[0] * m00, z01 = J0[0] * m10 + J0[1] * m11, z02 = J0[0] * m20 + J0[1] * m21 + J0[2] * m22;
     const double z10 = J1[0] * m00, z11 = J1[0] * m10 + J1[1] * m11, z12 = J1[0] * m20 + J1[1] * m21 + J1[2] * m22;
-    double e[18];
+    double e[20];
+    e[18] = 0.0; e[19] = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {           // E_theta = J_th^T Z ; E_t = -Jl^T Z
       e[3 * i + 0] = T0[i] * z00 + T1[i] * z10;
@@ -162,7 +175,7 @@ k_schur_E(int64_t n_obs, const int* __restrict__ obs_cam, const int* __restrict_
       e[9 + 3 * i + 2] = -(J0[i] * z02 + J1[i] * z12);
     }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Eo[k] = make_double2(e[2 * k], e[2 * k + 1]);
+    for (int k = 0; k < kEStride; k += 4) stg4(Eo + k, e[k], e[k + 1], e[k + 2], e[k + 3]);
   }
 }
 
@@ -190,12 +203,8 @@ k_schur_diag(const int* __restrict__ chunk_beg, const int* __restrict__ chunk_en
   for (int o = chunk_beg[ch] + lane; o < end; o += 32) {
     const int a = __ldg(cam_perm + o);
     const int l = __ldg(cobs_lm + o);
-    double e[18];
-#pragma unroll
-    for (int k = 0; k < 18; k += 2) {
-      const double2 x = ldg2(E + 18 * (size_t)a + k);
-      e[k] = x.x; e[k + 1] = x.y;
-    }
+    double e[20];
+    ldg_e(E + kEStride * (size_t)a, e);
     const double h0 = __ldg(hl + 3 * (size_t)l), h1 = __ldg(hl + 3 * (size_t)l + 1), h2 = __ldg(hl + 3 * (size_t)l + 2);
     int t = 0;
 #pragma unroll
@@ -296,14 +305,9 @@ k_schur_off(int64_t b_begin, int64_t n_blk, const int64_t* __restrict__ blk_ptr,
     for (int k = 0; k < 36; ++k) acc[k] = 0.0;
     for (int64_t p = blk_ptr[b]; p < blk_ptr[b + 1]; ++p) {
       const uint64_t ab = inc[p];
-      const double* Ea = E + 18 * (size_t)(ab >> 32);
-      const double* Eb = E + 18 * (size_t)(ab & 0xffffffffu);
-      double ea[18], eb[18];
-#pragma unroll
-      for (int k = 0; k < 18; k += 2) {
-        const double2 x = ldg2(Ea + k), y = ldg2(Eb + k);
-        ea[k] = x.x; ea[k + 1] = x.y; eb[k] = y.x; eb[k + 1] = y.y;
-      }
+      double ea[20], eb[20];
+      ldg_e(E + kEStride * (size_t)(ab >> 32), ea);
+      ldg_e(E + kEStride * (size_t)(ab & 0xffffffffu), eb);
 #pragma unroll
       for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -403,13 +407,8 @@ k_backsub(int n_lm, const int* __restrict__ lm_ptr, const int* __restrict__ obs_
         const double2 x = ldg2(yc + 6 * (size_t)c + k);
         y[k] = x.x; y[k + 1] = x.y;
       }
-      const double2* Eo = reinterpret_cast<const double2*>(E + 18 * (size_t)o);
-      double e[18];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const double2 x = __ldg(Eo + k);
-        e[2 * k] = x.x; e[2 * k + 1] = x.y;
-      }
+      double e[20];
+      ldg_e(E + kEStride * (size_t)o, e);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         w0 = fma(-e[3 * i], y[i], w0);
