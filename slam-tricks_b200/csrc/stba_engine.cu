@@ -208,6 +208,16 @@ struct Engine {
             const double* h_lm, const int32_t* h_oc, const int32_t* h_ol, const double* h_uv,
             const uint8_t* h_cc, const uint8_t* h_lc);
   int build_pairs();
+  // off-diagonal blocks [b0, b1) of the reduced system: one thread per block, or one warp per block when the incidence
+  // lists are few and long (>= 24 pairs per block on average: config B has ~200)
+  int launch_schur_off(int64_t b0, int64_t b1, double* out, int packed) {
+    if (n_blk > 0 && n_inc / n_blk >= 24)
+      k_schur_off_warp<<<grid_for(b1 - b0, kOffWarps), 32 * kOffWarps, 0, stream>>>(b0, b1, blk_ptr, inc, E, out, ld, packed);
+    else
+      k_schur_off<<<grid_for(b1 - b0, kBlock), kBlock, 0, stream>>>(b0, b1, blk_ptr, inc, E, out, ld, packed);
+    ++launches;
+    return STBA_OK;
+  }
   int set_state(const double* h_q, const double* h_t, const double* h_lm);
   int get_state(double* h_q, double* h_t, double* h_lm);
   int linearize();
@@ -602,7 +612,7 @@ int Engine::build_reduced(double radius, const stba_options& opt) {
     if (n_chunk)
       LAUNCH(this, k_schur_diag, n_chunk, 32, chunk_beg, chunk_end, cam_perm, cobs_lm, E, hl, chunk_acc);
     LAUNCH(this, k_schur_diag_finish, (n_cam + 127) / 128, 128, n_cam, cam_chunk_ptr, free_of, chunk_acc, Hcc, gc, Dc2, S, ld, rhs, 1, 0);
-    if (n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, (int64_t)0, n_blk, blk_ptr, inc, E, S, ld, 0);
+    if (n_blk) CKR(launch_schur_off(0, n_blk, S, 0));
   }
   CK(cudaGetLastError());
   reduced_built = true;
@@ -644,7 +654,7 @@ int Engine::reduce_linearization(double radius, const stba_options& opt) {
   // linearisation: the last range carries everything behind S.
   const int n_rng = (n_blk && red_chunks > 1 && n_free >= 64) ? red_chunks : 1;
   if (n_rng == 1) {
-    if (n_free && n_blk) LAUNCH(this, k_schur_off, grid_for(n_blk, kBlock), kBlock, (int64_t)0, n_blk, blk_ptr, inc, E, red, ld, 1);
+    if (n_free && n_blk) CKR(launch_schur_off(0, n_blk, red, 1));
     CKN(ncclAllReduce(red, red, red_count, ncclDouble, ncclSum, comm, stream));
   } else {
     if (!cstream) {
@@ -657,7 +667,7 @@ int Engine::reduce_linearization(double radius, const stba_options& opt) {
       int i_end = (c + 1 == n_rng) ? n_free : (int)(n_free * std::sqrt((double)(c + 1) / n_rng)) / 16 * 16;
       i_end = std::max(i_end, i_prev);
       const int64_t b0 = (int64_t)i_prev * (i_prev - 1) / 2, b1 = (int64_t)i_end * (i_end - 1) / 2;
-      if (b1 > b0) LAUNCH(this, k_schur_off, grid_for(b1 - b0, kBlock), kBlock, b0, b1, blk_ptr, inc, E, red, ld, 1);
+      if (b1 > b0) CKR(launch_schur_off(b0, b1, red, 1));
       CK(cudaEventRecord(cev[c], stream));
       CK(cudaStreamWaitEvent(cstream, cev[c], 0));
       const size_t r0 = 6 * (size_t)i_prev, r1 = 6 * (size_t)i_end;

@@ -337,6 +337,55 @@ k_schur_off(int64_t b_begin, int64_t n_blk, const int64_t* __restrict__ blk_ptr,
 // multi-GPU: the reduced packed lower triangle (row-major: (r, c <= r) at r (r + 1) / 2 + c) back into the
 // column-major S the factorisation works on, through a 32 x 32 shared-memory transpose (both sides coalesced).
 // grid: (tiles, tiles), tile (x = column tile, y = row tile), only y >= x does work.
+// schur_off for FEW, LONG incidence lists (config B: 1 128 blocks with ~200 pairs each — one thread per block left the
+// build at 0.55 ms, as long as at config C with twenty times the work): one WARP per block, lanes stride over the list,
+// the 36 per-lane sums are added in lane order through shared memory (fixed order: deterministic), lanes 0..35 write.
+constexpr int kOffWarps = 4;
+__global__ void __launch_bounds__(32 * kOffWarps)
+k_schur_off_warp(int64_t b_begin, int64_t n_blk, const int64_t* __restrict__ blk_ptr, const uint64_t* __restrict__ inc,
+                 const double* __restrict__ E, double* __restrict__ S, int n, int packed) {
+  __shared__ double s_red[kOffWarps][36][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t b = b_begin + (int64_t)blockIdx.x * kOffWarps + warp; b < n_blk; b += (int64_t)gridDim.x * kOffWarps) {
+    int64_t i = (int64_t)((1.0 + sqrt(1.0 + 8.0 * (double)b)) * 0.5);
+    while (i * (i - 1) / 2 > b) --i;
+    while ((i + 1) * i / 2 <= b) ++i;
+    const int64_t j = b - i * (i - 1) / 2;
+    double acc[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+    const int64_t end = blk_ptr[b + 1];
+    for (int64_t p = blk_ptr[b] + lane; p < end; p += 32) {
+      const uint64_t ab = inc[p];
+      double ea[20], eb[20];
+      ldg_e(E + kEStride * (size_t)(ab >> 32), ea);
+      ldg_e(E + kEStride * (size_t)(ab & 0xffffffffu), eb);
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+          acc[6 * c + r] = fma(ea[3 * r], eb[3 * c], fma(ea[3 * r + 1], eb[3 * c + 1], fma(ea[3 * r + 2], eb[3 * c + 2], acc[6 * c + r])));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 36; ++k) s_red[warp][k][lane] = acc[k];
+    __syncwarp();
+    for (int k = lane; k < 36; k += 32) {            // k = 6 c + r
+      double t = 0.0;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) t += s_red[warp][k][l];
+      const int c = k / 6, r = k % 6;
+      if (packed) {
+        const size_t row = 6 * i + r;
+        S[row * (row + 1) / 2 + 6 * j + c] = -t;
+      } else {
+        S[(size_t)(6 * i + r) + (size_t)(6 * j + c) * n] = -t;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(256) k_unpack_lower(const double* __restrict__ Sp, int n, double* __restrict__ S, int ld) {
   __shared__ double tile[32][33];
   const int tc = blockIdx.x, tr = blockIdx.y;
