@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/stba.h"
+#include "stba_pool.cuh"
 
 namespace {
 
@@ -507,6 +508,7 @@ int stba_calib_optimize_timed(int device, int32_t n_views, const int32_t* view_p
   for (int v = 0; v < n_views; ++v) se3_exp(poses + 6 * (size_t)v, &h_pose[12 * (size_t)v], &h_pose[12 * (size_t)v + 9]);
   memcpy(h_param.data(), intrinsics, 4 * sizeof(double));
   memcpy(h_param.data() + 4, distortion, 5 * sizeof(double));
+  stba::keep_default_pool(device);
   cudaStream_t s;
   CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   int* d_ptr = nullptr;

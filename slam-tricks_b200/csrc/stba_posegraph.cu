@@ -33,6 +33,7 @@
 
 #include "../../include/stba.h"
 #include "stba_chol.cuh"
+#include "stba_pool.cuh"
 
 namespace {
 
@@ -911,17 +912,19 @@ struct stba_pg {
   std::vector<void*> allocs;
   template <typename T>
   int alloc(T** p, size_t count) {
-    void* x = nullptr;
-    CK(cudaMalloc(&x, std::max<size_t>(count, 1) * sizeof(T)));
+    void* x = nullptr;      // stream-ordered, from the kept default pool: creating a graph per call costs no cudaMalloc / cudaFree stalls
+    CK(cudaMallocAsync(&x, (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255, s));
     allocs.push_back(x);
     *p = static_cast<T*>(x);
     return STBA_OK;
   }
   ~stba_pg() {
     chol.reset();
-    if (s) cudaStreamSynchronize(s);
-    for (void* p : allocs) cudaFree(p);
-    if (red_host) cudaFreeHost(red_host);
+    if (s) {
+      for (void* p : allocs) cudaFreeAsync(p, s);
+      cudaStreamSynchronize(s);
+    }
+    stba::pinned_blocks().put(red_host);
     if (s) cudaStreamDestroy(s);
   }
   static int band_smem(int b) { return (int)(((size_t)(b + 3) * (b + 1) * 36 + (size_t)(b + 1) * 36 + 36 + (size_t)(b + 3) * 6 + 6) * sizeof(double)); }
@@ -1025,6 +1028,7 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
   auto fail = [&](int r) { delete h; return r; };
 #define CKH(x) do { int r_ = (x); if (r_ != STBA_OK) return fail(r_); } while (0)
 #define CKD(x) do { if ((x) != cudaSuccess) return fail(STBA_ERR_CUDA); } while (0)
+  stba::keep_default_pool(device);
   CKD(cudaStreamCreateWithFlags(&h->s, cudaStreamNonBlocking));
   // (with loop closures the last separator group may reach past the last pose: B dummy identity columns behind it)
   const size_t N = (size_t)n_poses + (closure ? B : 0), M = std::max<int64_t>(n_edges, 1), CBn = (size_t)(B + 1) * 36;
@@ -1034,7 +1038,8 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
   CKH(h->alloc(&h->band, N * CBn)); CKH(h->alloc(&h->A, N * CBn)); CKH(h->alloc(&h->g, 6 * N)); CKH(h->alloc(&h->gs, 6 * N));
   CKH(h->alloc(&h->ys, 6 * N)); CKH(h->alloc(&h->scale, 6 * N)); CKH(h->alloc(&h->diag, 6 * N));
   CKH(h->alloc(&h->share, std::max(3 * N, (size_t)M))); CKH(h->alloc(&h->red, 8));
-  CKD(cudaMallocHost(&h->red_host, 8 * sizeof(double)));
+  h->red_host = stba::pinned_blocks().get();
+  if (!h->red_host) return fail(STBA_ERR_CUDA);
   CKD(cudaMemsetAsync(h->red, 0, 8 * sizeof(double), h->s));
   CKD(cudaMemsetAsync(h->ys, 0, 6 * N * sizeof(double), h->s));
   CKD(cudaMemsetAsync(h->gs, 0, 6 * N * sizeof(double), h->s));
@@ -1112,10 +1117,10 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
     // columns long (so that interiors never couple) and the reduced half-bandwidth 2B - 1 must fit the ring
     int P = 1;
     if (!getenv("STBA_PG_SERIAL") && 2 * B - 1 <= kMaxBand && n_poses >= 64 * B) {
-      cudaDeviceProp prop;
-      CKD(cudaGetDeviceProperties(&prop, device));
+      int sms = 0;                                   // (cudaGetDeviceProperties costs ~1 ms per call)
+      CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
       P = (int)std::lround(std::sqrt((double)n_poses / B));
-      P = std::max(1, std::min(P, prop.multiProcessorCount));
+      P = std::max(1, std::min(P, sms));
     }
     if (const char* ov = getenv("STBA_PG_PARTS")) P = (2 * B - 1 <= kMaxBand) ? std::max(1, atoi(ov)) : 1;    // tests: force a partition count
     while (P > 1 && (n_poses - (P - 1) * B) / P < std::max(B, 8)) --P;
