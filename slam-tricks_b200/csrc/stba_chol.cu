@@ -1909,6 +1909,7 @@ struct Dag2Params {
   int total_units;
   int W, G;
   int D;                    // tile rows k + 1 .. k + D are carried by dedicated CTAs at step k
+  int pick;                 // a worker claims one of the first `pick` ready candidates of a scan round (rows / tiles nearest the front come first)
   int R;                    // workers n_ded .. n_ded + R - 1 are RESERVED for tasks near the front (never start a long far update)
   const int* tiles;         // every tile (i | j << 16), column by column
   const int* col_start;     // col_start[j]: position of tile (j, j) in tiles[]
@@ -2350,7 +2351,7 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
       const unsigned m = __ballot_sync(FULL, ok0 || ok1);
       if (m) {
         const int cnt = __popc(m);
-        const int pick = __fns(m, 0, 1 + (wid % cnt));
+        const int pick = __fns(m, 0, 1 + (wid % min(cnt, P.pick)));
         int got = 0, hh = 0, kk = 0;
         if (lane == pick) {
           if (ok0 && atomicCAS(sv + 2 * i, ka, ka | ST_LOCK) == ka) { got = 1; hh = 2 * i; kk = ka; }
@@ -2414,7 +2415,7 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
           const unsigned m = __ballot_sync(FULL, ok);
           if (m) {
             const int cnt = __popc(m);
-            const int pick = __fns(m, 0, 1 + (wid % cnt));
+            const int pick = __fns(m, 0, 1 + (wid % min(cnt, P.pick)));
             int got = 0;
             if (lane == pick) got = (atomicCAS(st + (size_t)i * T + j, a, a | ST_LOCK) == a);
             got = __shfl_sync(FULL, got, pick);
@@ -2981,7 +2982,7 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
   Dag2Params dp;
   dp.S = P.S; dp.ld = ld; dp.n = n; dp.n_rows = n + 1; dp.T = T; dp.Tr = P.Tr; dp.R64 = P.R64;
   dp.Linv = P.Linv; dp.info = P.info; dp.flags = P.dflags;
-  dp.total_units = P.total_units; dp.W = P.W; dp.G = P.G; dp.D = P.D; dp.R = P.R;
+  dp.total_units = P.total_units; dp.W = P.W; dp.G = P.G; dp.D = P.D; dp.R = P.R; dp.pick = getenv("STBA_CHOL_PICK") ? std::max(1, atoi(getenv("STBA_CHOL_PICK"))) : 32;
   dp.tiles = P.d_tiles; dp.col_start = P.d_tiles + P.n_tiles; dp.n_tiles = P.n_tiles;
   dp.prof = P.prof; dp.trace = P.trace;
   void* args[] = {&dp};
@@ -3205,7 +3206,7 @@ static int split_launch_dag(const SplitPlan& P, double* S, int n, int T, double*
   Dag2Params dp;
   dp.S = S; dp.ld = P.ld; dp.n = n; dp.n_rows = n + 1; dp.T = T; dp.Tr = (n + 1 + NB - 1) / NB; dp.R64 = (n + 1 + 63) / 64;
   dp.Linv = Linv; dp.info = P.info; dp.flags = dflags;
-  dp.total_units = units; dp.W = P.W; dp.G = P.G; dp.D = P.D; dp.R = 0;
+  dp.total_units = units; dp.W = P.W; dp.G = P.G; dp.D = P.D; dp.R = 0; dp.pick = 32;
   dp.tiles = d_tiles; dp.col_start = d_tiles + n_tiles; dp.n_tiles = n_tiles;
   dp.prof = nullptr; dp.trace = nullptr;
   void* args[] = {&dp};
