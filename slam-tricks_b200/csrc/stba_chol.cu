@@ -1909,8 +1909,6 @@ struct Dag2Params {
   int total_units;
   int W, G;
   int D;                    // tile rows k + 1 .. k + D are carried by dedicated CTAs at step k
-  int pick;                 // a worker claims one of the first `pick` ready candidates of a scan round (rows / tiles nearest the front come first)
-  int R;                    // workers n_ded .. n_ded + R - 1 are RESERVED for tasks near the front (never start a long far update)
   const int* tiles;         // every tile (i | j << 16), column by column
   const int* col_start;     // col_start[j]: position of tile (j, j) in tiles[]
   int n_tiles;
@@ -2351,7 +2349,7 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
       const unsigned m = __ballot_sync(FULL, ok0 || ok1);
       if (m) {
         const int cnt = __popc(m);
-        const int pick = __fns(m, 0, 1 + (wid % min(cnt, P.pick)));
+        const int pick = __fns(m, 0, 1 + (wid % cnt));
         int got = 0, hh = 0, kk = 0;
         if (lane == pick) {
           if (ok0 && atomicCAS(sv + 2 * i, ka, ka | ST_LOCK) == ka) { got = 1; hh = 2 * i; kk = ka; }
@@ -2375,16 +2373,12 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
       const int j_start = min(ld_relaxed(P.flags + F2_JMIN), T);
       int jinc = 1 << 20;
       int c0 = P.col_start[j_start];
-      const int n_ded = 2 * P.D + P.D * (P.D + 1) - 1;
-      const bool reserved = wid < n_ded + P.R;
-      const int j_far = reserved ? min(np + P.W + 2, T) : T;      // a reserved worker looks no further than the window behind the front
-      const int c_stop = reserved ? P.col_start[j_far] : P.n_tiles;
-      for (; c0 < c_stop && !claimed; c0 += 128) {
+      for (; c0 < P.n_tiles && !claimed; c0 += 128) {
         int ti[4], tj[4], ta[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int c = c0 + 32 * u + lane;
-          const int e = c < c_stop ? __ldg(P.tiles + c) : -1;
+          const int e = c < P.n_tiles ? __ldg(P.tiles + c) : -1;
           ti[u] = e < 0 ? -1 : (e & 0xffff);
           tj[u] = e < 0 ? 0 : (e >> 16);
           ta[u] = e < 0 ? ST_LOCK : ld_relaxed(st + (size_t)ti[u] * T + tj[u]);
@@ -2415,7 +2409,7 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
           const unsigned m = __ballot_sync(FULL, ok);
           if (m) {
             const int cnt = __popc(m);
-            const int pick = __fns(m, 0, 1 + (wid % min(cnt, P.pick)));
+            const int pick = __fns(m, 0, 1 + (wid % cnt));
             int got = 0;
             if (lane == pick) got = (atomicCAS(st + (size_t)i * T + j, a, a | ST_LOCK) == a);
             got = __shfl_sync(FULL, got, pick);
@@ -2434,8 +2428,7 @@ __device__ __forceinline__ int4 find_task2(const Dag2Params& P, int wid, long lo
       }
       {
         // every tile before position c0 has been looked at: the hint may move up to the first incomplete column seen
-        const int c_seen = min(c0, c_stop);      // (a reserved worker stops at the window: nothing behind c_stop was looked at)
-        const int j_unseen = c_seen < P.n_tiles ? (__ldg(P.tiles + c_seen) >> 16) : T;
+        const int j_unseen = c0 < P.n_tiles ? (__ldg(P.tiles + c0) >> 16) : T;
         const int j_new = min(__reduce_min_sync(FULL, jinc), j_unseen);
         if (lane == 0 && j_new > j_start) atomicMax(P.flags + F2_JMIN, j_new);
       }
@@ -2644,7 +2637,7 @@ struct CholPlan {
   int dag_version = 2;        // 2: scan scheduler (default), 1: ticket queues (STBA_CHOL_DAG1=1)
   cudaStream_t pool_stream = nullptr;   // DAG 2: every buffer is stream-ordered (pooled): no cudaMalloc / cudaFree stalls per problem
   int* d_tiles = nullptr;     // DAG 2: tile list + column starts
-  int n_tiles = 0, total_units = 0, W = 2, G = 8, D = 1, R = 0;
+  int n_tiles = 0, total_units = 0, W = 2, G = 8, D = 1;
   long long* prof = nullptr;
   unsigned long long* trace = nullptr;
   cudaStream_t side = nullptr, inv = nullptr;
@@ -2932,7 +2925,6 @@ static int build_dag2_plan(CholPlan& P, cudaStream_t stream) {
   if (const char* s = getenv("STBA_CHOL_DEPTH")) P.D = std::max(1, std::min(4, atoi(s)));
   if (const char* s = getenv("STBA_CHOL_WINDOW")) P.W = std::max(0, atoi(s));
   if (const char* s = getenv("STBA_CHOL_AGG")) P.G = std::max(1, std::min(16, atoi(s)));
-  if (const char* s = getenv("STBA_CHOL_RESERVE")) P.R = std::max(0, atoi(s));
   std::vector<int> tiles, col_start(T + 1, 0);
   long long units = T;                               // the inverse completions
   for (int j = 0; j < T; ++j) {
@@ -2982,7 +2974,7 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
   Dag2Params dp;
   dp.S = P.S; dp.ld = ld; dp.n = n; dp.n_rows = n + 1; dp.T = T; dp.Tr = P.Tr; dp.R64 = P.R64;
   dp.Linv = P.Linv; dp.info = P.info; dp.flags = P.dflags;
-  dp.total_units = P.total_units; dp.W = P.W; dp.G = P.G; dp.D = P.D; dp.R = P.R; dp.pick = getenv("STBA_CHOL_PICK") ? std::max(1, atoi(getenv("STBA_CHOL_PICK"))) : 32;
+  dp.total_units = P.total_units; dp.W = P.W; dp.G = P.G; dp.D = P.D;
   dp.tiles = P.d_tiles; dp.col_start = P.d_tiles + P.n_tiles; dp.n_tiles = P.n_tiles;
   dp.prof = P.prof; dp.trace = P.trace;
   void* args[] = {&dp};
@@ -3206,7 +3198,7 @@ static int split_launch_dag(const SplitPlan& P, double* S, int n, int T, double*
   Dag2Params dp;
   dp.S = S; dp.ld = P.ld; dp.n = n; dp.n_rows = n + 1; dp.T = T; dp.Tr = (n + 1 + NB - 1) / NB; dp.R64 = (n + 1 + 63) / 64;
   dp.Linv = Linv; dp.info = P.info; dp.flags = dflags;
-  dp.total_units = units; dp.W = P.W; dp.G = P.G; dp.D = P.D; dp.R = 0; dp.pick = 32;
+  dp.total_units = units; dp.W = P.W; dp.G = P.G; dp.D = P.D;
   dp.tiles = d_tiles; dp.col_start = d_tiles + n_tiles; dp.n_tiles = n_tiles;
   dp.prof = nullptr; dp.trace = nullptr;
   void* args[] = {&dp};
