@@ -136,6 +136,7 @@ struct Engine {
   double* flush_buf = nullptr;
   size_t flush_n = 0;
   cudaEvent_t ev[PH_COUNT + 1] = {};
+  cudaEvent_t evl[2] = {};              // linearisation of an accepted step whose scalars are read with the NEXT iteration's (deferred)
   ncclComm_t comm = nullptr;
   bool comm_owned = true;      // false: attached with stba_ba_use_comm, lives in a stba_comm handle
   int rank = 0, nranks = 1;
@@ -196,6 +197,8 @@ struct Engine {
     }
     if (scal_host) { std::lock_guard<std::mutex> lk(g_pinned_mu); g_pinned_free.push_back(scal_host); }
     for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : evl)
       if (e) cudaEventDestroy(e);
     for (auto& e : cev)
       if (e) cudaEventDestroy(e);
@@ -308,6 +311,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   max_grid = sm_count * 16;
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto& e : ev) CK(cudaEventCreate(&e));
+  for (auto& e : evl) CK(cudaEventCreate(&e));
   n_cam = ncam; n_lm = nlm; n_obs = nobs;
 
   tr.mark("stream/events/attrs");
@@ -826,8 +830,39 @@ int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_cal
     term = STBA_FAILURE; msg = "Initial residual evaluation is not finite.";
   }
 
+  // ONE host read per iteration: after an accepted step the cost and gradient norms of the new linearisation are not
+  // waited for — they arrive with the scalars of the NEXT step, which is enqueued speculatively (it only writes the
+  // candidate buffers).  The iteration record is patched then; if the gradient tolerance turns out to be met the
+  // speculative step is dropped.  Callbacks, progress printing and the multi-GPU path keep the synchronous order.
+  const bool defer_ok = !cb && !opt.minimizer_progress_to_stdout && nranks == 1 && !getenv("STBA_LM_SYNC");
+  bool pending = false;
+  int pending_rec = -1;
+  auto resolve_pending = [&]() {          // scal_host holds the scalars of the deferred linearisation
+    add_phase(PH_LIN, evl[0], evl[1]);
+    x_cost = scal_host[SC_COST];
+    const double gn = std::sqrt(scal_host[SC_G2]), gm = scal_host[SC_GMAX];
+    if (sum && sum->iterations && pending_rec >= 0 && pending_rec < sum->iterations_capacity) {
+      sum->iterations[pending_rec].cost = x_cost;
+      sum->iterations[pending_rec].gradient_norm = gn;
+      sum->iterations[pending_rec].gradient_max_norm = gm;
+    }
+    min_cost = std::min(min_cost, x_cost);
+    it.cost = x_cost; it.gradient_norm = gn; it.gradient_max_norm = gm;
+    pending = false;
+    return gm;
+  };
+
   while (term != STBA_FAILURE || n_rec == 0) {
     // ---- FinalizeIterationAndCheckIfMinimizerCanContinue ----
+    if (pending && (it.iteration >= opt.max_num_iterations || radius < opt.min_trust_region_radius)) {
+      // this record is the last one: no next step to ride along with
+      CKR(fetch_scalars());
+      const int keep = pending_rec;
+      pending_rec = -1;                   // (the record is written below, from `it`)
+      resolve_pending();
+      pending_rec = keep;
+    }
+    if (pending) pending_rec = n_rec;
     if (it.step_is_successful) ++n_succ; else ++n_unsucc;
     it.trust_region_radius = radius;
     it.iteration_time_ms = std::chrono::duration<double, std::milli>(clk::now() - t_iter).count();
@@ -846,7 +881,7 @@ int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_cal
       if (r == STBA_SOLVER_TERMINATE_SUCCESSFULLY) { term = STBA_USER_SUCCESS; msg = "User callback returned SOLVER_TERMINATE_SUCCESSFULLY."; break; }
     }
     if (it.iteration >= opt.max_num_iterations) { term = STBA_NO_CONVERGENCE; msg = "Maximum number of iterations reached."; break; }
-    if (it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) { term = STBA_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
+    if (!pending && it.step_is_successful && it.gradient_max_norm <= opt.gradient_tolerance) { term = STBA_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
     if (radius < opt.min_trust_region_radius) { term = STBA_CONVERGENCE; msg = "Minimum trust region radius reached."; break; }
 
     stba_iteration prev = it;
@@ -869,6 +904,11 @@ int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_cal
     CKR(fetch_scalars());
     add_phase(PH_SCHUR, ev[0], ev[1]); add_phase(PH_DENSE, ev[1], ev[2]);
     add_phase(PH_BACKSUB, ev[2], ev[3]); add_phase(PH_COST, ev[3], ev[4]);
+    if (pending) {
+      // the accepted point's scalars came along: patch its record; a met gradient tolerance ends the solve there
+      // (the step just computed is dropped: it lives in the candidate buffers only)
+      if (resolve_pending() <= opt.gradient_tolerance) { term = STBA_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
+    }
 
     const double mcc = 0.5 * (scal_host[SC_MCC_C] + scal_host[SC_MCC_L]);   // model cost change
     const double cand_cost = scal_host[SC_CAND];
@@ -910,16 +950,26 @@ int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_cal
       x_norm = std::sqrt(scal_host[SC_XN2_C] + scal_host[SC_XN2_L]);
       radius = std::min(opt.max_trust_region_radius, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
       decrease_factor = 2.0;
-      CK(cudaEventRecord(ev[0], stream));
-      CKR(linearize());
-      if (nranks > 1) CKR(build_reduced(radius, opt));      // ONE collective: S | rhs | H_cc | g_c | cost | gradient norms
-      else CKR(post_linearize(opt, true));
-      CK(cudaEventRecord(ev[1], stream));
-      CKR(fetch_scalars());
-      add_phase(PH_LIN, ev[0], ev[1]);
-      x_cost = scal_host[SC_COST];
-      it.cost = x_cost; it.gradient_norm = std::sqrt(scal_host[SC_G2]); it.gradient_max_norm = scal_host[SC_GMAX];
-      it.step_is_successful = 1;
+      if (defer_ok) {
+        CK(cudaEventRecord(evl[0], stream));
+        CKR(linearize());
+        CKR(post_linearize(opt, true));
+        CK(cudaEventRecord(evl[1], stream));
+        pending = true;                                      // cost / gradient norms: with the next step's scalars
+        it.cost = cand_cost;                                 // (= the new cost up to the summation order; patched exactly later)
+        it.step_is_successful = 1;
+      } else {
+        CK(cudaEventRecord(ev[0], stream));
+        CKR(linearize());
+        if (nranks > 1) CKR(build_reduced(radius, opt));      // ONE collective: S | rhs | H_cc | g_c | cost | gradient norms
+        else CKR(post_linearize(opt, true));
+        CK(cudaEventRecord(ev[1], stream));
+        CKR(fetch_scalars());
+        add_phase(PH_LIN, ev[0], ev[1]);
+        x_cost = scal_host[SC_COST];
+        it.cost = x_cost; it.gradient_norm = std::sqrt(scal_host[SC_G2]); it.gradient_max_norm = scal_host[SC_GMAX];
+        it.step_is_successful = 1;
+      }
     } else {
       it.cost = cand_ok ? cand_cost : x_cost;
       radius /= decrease_factor;
@@ -927,6 +977,10 @@ int Engine::solve(const stba_options& opt, stba_summary* sum, stba_iteration_cal
     }
   }
 
+  if (pending) {                          // (defensive: every path above resolves it)
+    CKR(fetch_scalars());
+    resolve_pending();
+  }
   if (sum) {
     sum->termination_type = term;
     sum->num_iterations = std::min(n_rec, sum->iterations ? sum->iterations_capacity : n_rec);
