@@ -312,6 +312,8 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto& e : ev) CK(cudaEventCreate(&e));
   for (auto& e : evl) CK(cudaEventCreate(&e));
+  CK(cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking));      // uploads that overlap the preprocessing; multi-GPU: the ranged reduction
+  for (auto& e2 : cev) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
   n_cam = ncam; n_lm = nlm; n_obs = nobs;
 
   tr.mark("stream/events/attrs");
@@ -362,7 +364,13 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
   tr.mark("cudaMalloc");
   CK(cudaMemcpyAsync(obs_cam, h_oc, nobs * sizeof(int), cudaMemcpyDefault, stream));
   CK(cudaMemcpyAsync(obs_lm, h_ol, nobs * sizeof(int), cudaMemcpyDefault, stream));
-  CK(cudaMemcpyAsync(obs_uv, h_uv, 2 * nobs * sizeof(double), cudaMemcpyDefault, stream));
+  // the measurements (16 of the 24 bytes per observation) are not needed before the camera-major copy is gathered: they
+  // travel on the communication stream while the index ranges are validated and the degree / CSR kernels run
+  // (pinned source: ~0.3 ms of PCIe time at config C off the create path; pageable source: staged synchronously, no harm)
+  CK(cudaEventRecord(cev[0], stream));                       // (obs_uv was allocated on `stream`: order the copy behind it)
+  CK(cudaStreamWaitEvent(cstream, cev[0], 0));
+  CK(cudaMemcpyAsync(obs_uv, h_uv, 2 * nobs * sizeof(double), cudaMemcpyDefault, cstream));
+  CK(cudaEventRecord(cev[1], cstream));
   CK(cudaMemcpyAsync(cam_const, h_const.data(), ncam, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(free_of, h_free.data(), ncam * sizeof(int), cudaMemcpyHostToDevice, stream));
   if (has_lm_const) CK(cudaMemcpyAsync(lm_const, h_lc, nlm, cudaMemcpyHostToDevice, stream));
@@ -398,6 +406,7 @@ int Engine::setup(int dev, int32_t ncam, int32_t nlm, int64_t nobs, const double
     CK(cudaMemsetAsync(cursor, 0, ncam * sizeof(int), stream));
     LAUNCH(this, k_bucket_scatter, grid_for(nobs, 256), 256, nobs, obs_cam, cam_ptr, cursor, cam_perm);
     LAUNCH(this, k_sort_buckets_i32, std::min(ncam, max_grid), 256, ncam, cam_ptr, cam_perm);
+    CK(cudaStreamWaitEvent(stream, cev[1], 0));              // the measurements have arrived
     LAUNCH(this, k_gather_cam_major, grid_for(nobs, 256), 256, nobs, cam_perm, obs_lm, obs_uv, cobs_lm, cobs_uv);
   }
 
