@@ -497,7 +497,7 @@ k_pg_part_rhs(int B, int P, const int* __restrict__ pi0, const int* __restrict__
               const double* __restrict__ y, double* __restrict__ Z) {
   const int p = blockIdx.x, i0 = pi0[p], i1 = pi1[p], CB = (B + 1) * 36, Rw = 1 + 12 * B;
   const int total = (i1 - i0) * 6 * Rw;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < total; e += blockDim.x * gridDim.y) {      // grid (P, S): S CTAs share an interior
     const int c = i0 + e / (6 * Rw), a = (e / Rw) % 6, col = e % Rw;
     double v = 0.0;
     if (col == 0) {
@@ -635,9 +635,12 @@ k_pg_part_factor(int B, const int* __restrict__ pi0, const int* __restrict__ pi1
 // G_p = Z_p^T Z_p  (Rw x Rw), rows streamed through shared memory in tiles of 32
 __global__ void __launch_bounds__(256)
 k_pg_part_gram(int B, const int* __restrict__ pi0, const int* __restrict__ pi1, const double* __restrict__ Z, double* __restrict__ G) {
+  // grid (P, S): with fewer interiors than SMs the rows of an interior are cut into S = gridDim.y slices, one CTA each; the
+  // slices' Gram matrices land in G[(p * S + slice)] and k_pg_gram_sum adds them in slice order (S = 1: G is final)
   extern __shared__ __align__(16) double sm[];          // tile[32][Rw]
-  const int p = blockIdx.x, Rw = 1 + 12 * B, rows = 6 * (pi1[p] - pi0[p]);
-  const double* Zp = Z + (size_t)pi0[p] * 6 * Rw;
+  const int p = blockIdx.x, S = gridDim.y, part = blockIdx.y, Rw = 1 + 12 * B, rows_all = 6 * (pi1[p] - pi0[p]);
+  const int per = ((rows_all + S - 1) / S + 5) / 6 * 6, r_lo = min(rows_all, part * per), rows = min(rows_all, r_lo + per) - r_lo;
+  const double* Zp = Z + (size_t)pi0[p] * 6 * Rw + (size_t)r_lo * Rw;
   const int n_ent = Rw * Rw;
   constexpr int MAXE = 40;                              // entries per thread: Rw^2 / 256 <= 9409 / 256 for B = 8
   double acc[MAXE];
@@ -662,7 +665,15 @@ k_pg_part_gram(int B, const int* __restrict__ pi0, const int* __restrict__ pi1, 
 #pragma unroll
   for (int k = 0; k < MAXE; ++k) {
     const int e = threadIdx.x + 256 * k;
-    if (e < n_ent) G[(size_t)p * n_ent + e] = acc[k];
+    if (e < n_ent) G[((size_t)p * S + part) * n_ent + e] = acc[k];
+  }
+}
+__global__ void __launch_bounds__(256) k_pg_gram_sum(int n_ent, int S, const double* __restrict__ Gs, double* __restrict__ G) {
+  const int p = blockIdx.x;
+  for (int e = threadIdx.x; e < n_ent; e += 256) {
+    double t = Gs[((size_t)p * S) * n_ent + e];
+    for (int q = 1; q < S; ++q) t += Gs[((size_t)p * S + q) * n_ent + e];
+    G[(size_t)p * n_ent + e] = t;
   }
 }
 
@@ -902,7 +913,8 @@ struct stba_pg {
   // partitioned band solve (P > 1): interiors [pi0, pi1), separators of B columns in between
   int P = 1, Br = 1;
   int *pi0 = nullptr, *pi1 = nullptr;
-  double *Z = nullptr, *G = nullptr, *Rb = nullptr, *yR = nullptr;
+  double *Z = nullptr, *G = nullptr, *Rb = nullptr, *yR = nullptr, *Gs = nullptr;
+  int gram_split = 1;        // row slices per interior of the spike Gram kernel (fewer interiors than SMs)
   // loop closures (edges longer than the band): endpoints live in separator groups, the reduced system is dense
   bool closure = false;
   int n_cl = 0, n_red = 0, ld_red = 0;
@@ -940,9 +952,15 @@ struct stba_pg {
       return STBA_OK;
     }
     const int Rw = 1 + 12 * B;
-    k_pg_part_rhs<<<P, 256, 0, s>>>(B, P, pi0, pi1, A, ys, Z);
+    k_pg_part_rhs<<<dim3(P, gram_split), 256, 0, s>>>(B, P, pi0, pi1, A, ys, Z);
     k_pg_part_factor<<<P, BS_THREADS, factor_smem(), s>>>(B, pi0, pi1, A, Z, info);
-    k_pg_part_gram<<<P, 256, 32 * Rw * (int)sizeof(double), s>>>(B, pi0, pi1, Z, G);
+    if (gram_split > 1) {
+      k_pg_part_gram<<<dim3(P, gram_split), 256, 32 * Rw * (int)sizeof(double), s>>>(B, pi0, pi1, Z, Gs);
+      k_pg_gram_sum<<<P, 256, 0, s>>>(Rw * Rw, gram_split, Gs, G);
+      ++launches;
+    } else {
+      k_pg_part_gram<<<P, 256, 32 * Rw * (int)sizeof(double), s>>>(B, pi0, pi1, Z, G);
+    }
     if (closure) {
       CK(cudaMemsetAsync(R, 0, (size_t)ld_red * n_red * sizeof(double), s));
       CK(cudaMemsetAsync(info2, 0, sizeof(int), s));
@@ -1134,6 +1152,12 @@ int stba_pg_create(stba_pg** out, int device, int32_t n_poses, int64_t n_edges, 
       const size_t Rw = 1 + 12 * (size_t)B;
       CKH(h->alloc(&h->pi0, P)); CKH(h->alloc(&h->pi1, P));
       CKH(h->alloc(&h->Z, N * 6 * Rw)); CKH(h->alloc(&h->G, (size_t)P * Rw * Rw));
+      {
+        int sms = 0;
+        CKD(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        h->gram_split = std::max(1, std::min(4, (sms + P / 2) / P));
+        if (h->gram_split > 1) CKH(h->alloc(&h->Gs, (size_t)P * h->gram_split * Rw * Rw));
+      }
       CKH(h->alloc(&h->Rb, (size_t)(P - 1) * B * (h->Br + 1) * 36)); CKH(h->alloc(&h->yR, (size_t)(P - 1) * B * 6));
       CKD(cudaMemcpyAsync(h->pi0, i0.data(), P * sizeof(int), cudaMemcpyHostToDevice, h->s));
       CKD(cudaMemcpyAsync(h->pi1, i1.data(), P * sizeof(int), cudaMemcpyHostToDevice, h->s));
