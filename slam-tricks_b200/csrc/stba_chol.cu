@@ -1217,7 +1217,10 @@ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 constexpr int DAG_SMEM = cmax(cmax(TS_SMEM, POTRF_SMEM), cmax(UPD_SMEM, cmax(TU_SMEM, PROG_SMEM)));
 enum { TASK_EXIT = -1, TASK_TRSM = 0, TASK_UPD = 1, TASK_INV = 2, TASK_UPD64 = 3 };
 enum { F_HP = 0, F_LP = 32, F_ABORT = 64, F_NPAN = 96, F_UR = 128, F_PDONE = 160 };     // queue heads and the abort flag on their own 128-byte lines
-constexpr long long SPIN_LIMIT = 1ll << 21;     // ~ seconds; a broken schedule must never hang the device
+#ifndef STBA_SPIN_SHIFT
+#define STBA_SPIN_SHIFT 21
+#endif
+constexpr long long SPIN_LIMIT = 1ll << STBA_SPIN_SHIFT;     // ~ seconds; a broken schedule must never hang the device
 
 struct DagParams {
   double* S;
