@@ -74,6 +74,58 @@ def test_linearize_blocks_match_oracle(stba, bo, fix, request):
     assert np.all(H2[sc.cam_const.astype(bool)] == 0) and np.all(g2[sc.cam_const.astype(bool)] == 0)
 
 
+def _blocks_equal_oracle(stba, bo, sc):
+    r, Jc, Jl = bo.residual_jacobian(sc.cam_q, sc.cam_t, sc.lm, sc.obs_cam, sc.obs_lm, sc.obs_uv)
+    Hcc, gc, Hll, gl, W = bo.normal_blocks(r, Jc, Jl, sc.obs_cam, sc.obs_lm, sc.n_cam, sc.n_lm, sc.cam_const)
+    with stba.engine.BAEngine(sc.cam_q, sc.cam_t, sc.lm, sc.obs_cam, sc.obs_lm, sc.obs_uv, sc.cam_const, linearize_only=True) as e:
+        e.linearize()
+        first = e.blocks()
+        e.linearize()                       # the ticket counters and the chunk queue re-arm themselves
+        H2, g2, Hl2, gl2, cost = e.blocks()
+    assert all(np.array_equal(a, b) for a, b in zip(first[:4], (H2, g2, Hl2, gl2))) and first[4] == cost      # bit-reproducible
+    _close(H2, Hcc, BLOCK_RTOL, "Hcc"); _close(g2, gc, BLOCK_RTOL, "gc")
+    _close(Hl2, Hll, BLOCK_RTOL, "Hll"); _close(gl2, gl, BLOCK_RTOL, "gl")
+    assert abs(cost - 0.5 * np.sum(r * r)) <= 1e-13 * cost
+
+
+def _tile_scene(sc, k):
+    """k side-by-side copies of a scene (cameras, landmarks and observations renumbered): the layout of bench.py's
+    `roofline_scaled` workload."""
+    import types
+    rep = lambda a, shift: (a[None, :] + (np.arange(k) * shift)[:, None]).astype(np.int32).ravel()
+    return types.SimpleNamespace(cam_q=np.tile(sc.cam_q, (k, 1)), cam_t=np.tile(sc.cam_t, (k, 1)), lm=np.tile(sc.lm, (k, 1)),
+                                 obs_cam=rep(sc.obs_cam, sc.n_cam), obs_lm=rep(sc.obs_lm, sc.n_lm), obs_uv=np.tile(sc.obs_uv, (k, 1)),
+                                 cam_const=np.tile(sc.cam_const, k), n_cam=k * sc.n_cam, n_lm=k * sc.n_lm)
+
+
+def test_linearize_camera_window_restaging(stba, bo):
+    """More than 1024 cameras: the landmark group of k_lin3 holds a window of the camera tiles in shared memory and
+    re-stages it when a chunk's camera range leaves it — three copies of a 400-camera scene (1200 cameras; every CTA's
+    range of landmark chunks crosses at most a copy boundary)."""
+    _blocks_equal_oracle(stba, bo, _tile_scene(stba.synth.make_scene(400, 3000, 24000), 3))
+
+
+def test_linearize_chunk_wider_than_a_window(stba, bo):
+    """Landmarks that see cameras more than 1024 indices apart (a chunk's camera range does not fit a window): the tiles of
+    that chunk are gathered from global memory."""
+    sc = _tile_scene(stba.synth.make_scene(600, 400, 4000), 2)
+    # tie the two copies together: every tenth observation of copy 0 goes to the same camera of copy 1 (range > 1024 in its chunk)
+    oc = sc.obs_cam.copy()
+    first = np.arange(len(oc) // 2)
+    move = first[::10]
+    oc[move] += 600
+    # keep (camera, landmark) pairs unique and the stream landmark-major (observation order inside a landmark is free)
+    sc.obs_cam = oc
+    assert len(set(zip(sc.obs_cam.tolist(), sc.obs_lm.tolist()))) == len(oc)
+    _blocks_equal_oracle(stba, bo, sc)
+
+
+def test_linearize_chunk_larger_than_a_stage(stba, bo):
+    """128 consecutive landmarks with more than 1536 observations: the chunk's stream is read from global memory instead
+    of the TMA-staged copy (and one-warp camera chunks with a single short round)."""
+    _blocks_equal_oracle(stba, bo, stba.synth.make_scene(200, 200, 3600))      # 18 observations per landmark: 2304 per chunk
+
+
 def _oracle_system(bo, sc):
     r, Jc, Jl = bo.residual_jacobian(sc.cam_q, sc.cam_t, sc.lm, sc.obs_cam, sc.obs_lm, sc.obs_uv)
     Hcc, gc, Hll, gl, W = bo.normal_blocks(r, Jc, Jl, sc.obs_cam, sc.obs_lm, sc.n_cam, sc.n_lm, sc.cam_const)
