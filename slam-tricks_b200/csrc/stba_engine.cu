@@ -490,7 +490,8 @@ int Engine::build_pairs() {
   if (n_inc) {
     CK(cudaMemsetAsync(cnt, 0, n_blk * sizeof(int), stream));
     LAUNCH(this, (k_pair_pass<1>), grid_for(n_lm, 128), 128, n_lm, lm_ptr, obs_cam, free_of, lc, cnt, blk_ptr, inc, dup_flag);
-    LAUNCH(this, k_sort_segments_u64, grid_for(n_blk, kBlock / 32), kBlock, n_blk, blk_ptr, inc);
+    LAUNCH(this, k_sort_segments_16, grid_for(n_blk, kBlock / 16), kBlock, n_blk, blk_ptr, inc);
+    LAUNCH(this, k_sort_segments_u64, grid_for(n_blk, kBlock / 32), kBlock, n_blk, blk_ptr, inc, 1);
   }
   CK(cudaStreamSynchronize(stream));
   return STBA_OK;
