@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 namespace stba {
@@ -2620,6 +2621,10 @@ static int substitution_chunk() {
 
 }  // namespace
 
+}  // namespace stba
+#include "stba_chol_small.cuh"
+namespace stba {
+
 struct CholPlan {
   double* S = nullptr;
   double* rhs = nullptr;
@@ -3037,6 +3042,29 @@ static int run_dag2(CholPlan& P, cudaStream_t stream) {
 int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, int* dev_info, cudaStream_t stream, int* n_launches) {
   if (n <= 0) return STBA_OK;
   if (ld % 2 || ld < n + 1) return STBA_ERR_UNSUPPORTED;   // 16-byte cp.async rows; room for the rhs row
+  {
+    // small systems: one launch of one CTA (stba_chol_small.cuh); STBA_CHOL_SMALL_N=0 sends everything to the DAG kernel
+    static const int small_n = std::min(CS_MAXN, getenv("STBA_CHOL_SMALL_N") ? atoi(getenv("STBA_CHOL_SMALL_N")) : CS_DEFAULT_N);
+    if (n <= small_n) {
+      static std::once_flag once;
+      static cudaError_t attr_rc = cudaSuccess;
+      std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM); });
+      CKC(attr_rc);
+      k_chol_small<<<1, CS_THREADS, CS_SMEM, stream>>>(S, ld, n, rhs, dev_info);
+      CKC(cudaGetLastError());
+#ifdef STBA_CS_TIMING
+      {
+        cudaStreamSynchronize(stream);
+        long long h[16];
+        cudaMemcpyFromSymbol(h, g_cs_clk, sizeof(h));
+        fprintf(stderr, "[chol small n=%d] cycles: init+potf2 %lld | panel solve %lld | rhs row %lld tile00 %lld load %lld potf2 %lld tiles %lld barrier %lld | bwd gemv %lld bwd solve %lld\n",
+                n, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+      }
+#endif
+      if (n_launches) *n_launches += 1;
+      return STBA_OK;
+    }
+  }
   CholPlan* P = ws.plan;
   if (!P || P->S != S || P->n != n || P->ld != ld || P->rhs != rhs || P->info != dev_info) {
     destroy_plan(P);

@@ -1,0 +1,258 @@
+// Dense reduced-camera solve for SMALL systems (n <= 512: BASELINE configs[1], 50 cameras -> n = 288; PnP-sized and
+// calibration-sized Schur complements): ONE launch, ONE CTA.
+//
+// The 128-block DAG kernel (k_chol_dag2) needs three panel steps at n = 288 and each of them is a chain of one-CTA
+// tasks (diagonal block 128 x 128, panel solve, tile update) with a flag round trip in between: 0.21 ms, of which the
+// machine is one SM wide almost all the time.  A matrix this small is better served by one CTA that never leaves its
+// SM: 32-column panels, the factored panel X kept in shared memory (k-major, so that the DMMA fragments of the
+// trailing update are conflict-free 8-byte loads), the trailing matrix updated in place in L2 by 32 x 32 warp tiles
+// on the FP64 tensor pipe (mma.sync.m8n8k4.f64), the right-hand side riding along as row n of S (forward substitution
+// for free), the backward substitution by 32-blocks at the end.  Look-ahead: warp 0 factorises the next diagonal block
+// while the other warps are still updating the rest of the trailing matrix.
+// Fixed summation orders, no atomics on data: bit-reproducible.  Same contract as chol_factor_solve (stba_chol.cuh).
+#pragma once
+
+namespace stba {
+namespace {
+
+constexpr int CS_B = 32;                       // panel width
+constexpr int CS_THREADS = 512;
+constexpr int CS_MAXN = 512;                   // largest n served (rows below a panel: n + 1 - 32 <= 481 threads)
+constexpr int CS_DEFAULT_N = 320;               // systems up to this order take this path (measured: 0.166 ms against 0.205 ms at n = 288, 0.267 against 0.216 at n = 384; STBA_CHOL_SMALL_N overrides)
+constexpr int CS_LDX = CS_MAXN + 4;            // k-major panel: (q * CS_LDX + g) mod 16 distinct for q, g < 4 (8-byte banks)
+constexpr int CS_LDD = CS_B + 1;               // diagonal block, row-major, padded
+constexpr int CS_SMEM = (CS_B * CS_LDX + 2 * CS_B * CS_LDD + 2 * CS_B + CS_MAXN + 8) * (int)sizeof(double);
+
+// Cholesky of the 32 x 32 block in D (row-major, ld CS_LDD, lower part valid, identity-padded), by ONE warp, lane =
+// row, left-looking: column j = (a_ij - sum_{c<j} l_ic l_jc) / l_jj with the own row in registers and row j read from
+// shared memory (broadcast).  invd[j] = 1 / l_jj.  Returns the 1-based index of the first non-positive pivot or 0.
+__device__ __noinline__ int cs_potf2_warp(double* D, double* invd, int lane) {
+  // (own row in registers, fully unrolled: a rolled variant with the row in shared memory measured 2 x slower —
+  // every term of the dependent chain then waits for two shared-memory loads)
+  double a[CS_B];
+#pragma unroll
+  for (int c = 0; c < CS_B; ++c) a[c] = D[lane * CS_LDD + c];
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < CS_B; ++j) {
+    double v0 = a[j], v1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < j; ++c) {
+      const double l = D[j * CS_LDD + c];
+      if (c & 1) v1 = fma(-a[c], l, v1);
+      else v0 = fma(-a[c], l, v0);
+    }
+    const double v = v0 + v1;
+    const double d = __shfl_sync(0xffffffffu, v, j);
+    if (!(d > 0.0) && !bad) bad = j + 1;
+    const double rs = fast_rsqrt(d);
+    a[j] = lane == j ? d * rs : (lane > j ? v * rs : 0.0);
+    if (lane >= j) D[lane * CS_LDD + j] = a[j];
+    if (lane == j) invd[j] = rs;
+    __syncwarp();
+  }
+  return bad;
+}
+
+#ifdef STBA_CS_TIMING
+__device__ long long g_cs_clk[16];
+#define CSTICK(slot) do { if (tid == 0) { const long long now_ = clock64(); g_cs_clk[slot] += now_ - t_last; t_last = now_; } } while (0)
+#else
+#define CSTICK(slot) do {} while (0)
+#endif
+
+__global__ void __launch_bounds__(CS_THREADS, 1)
+k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, int* __restrict__ info) {
+  extern __shared__ __align__(16) double cs_sm[];
+  double* Xt = cs_sm;                              // [32][CS_LDX]: X^T of the current panel (rows below the diagonal block)
+  double* Dbuf = Xt + CS_B * CS_LDX;               // two diagonal blocks (current, next)
+  double* invbuf = Dbuf + 2 * CS_B * CS_LDD;       // their inverse diagonals
+  double* xs = invbuf + 2 * CS_B;                  // backward substitution: solution so far
+  int* s_bad = reinterpret_cast<int*>(xs + CS_MAXN);
+  int* s_next = s_bad + 1;                         // ticket of the trailing-update tiles
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;           // DMMA fragment coordinates
+
+#ifdef STBA_CS_TIMING
+  long long t_last = clock64();
+  if (tid == 0) for (int k = 0; k < 16; ++k) g_cs_clk[k] = 0;
+#endif
+  if (tid == 0) *s_bad = 0;
+  for (int c = tid; c < n; c += CS_THREADS) S[(size_t)c * ld + n] = rhs[c];      // the augmented row
+  // first diagonal block
+  auto load_diag = [&](int k0, double* D, int t0, int nthreads) {
+    const int nb = min(CS_B, n - k0);
+    for (int idx = t0; idx < CS_B * CS_B; idx += nthreads) {
+      const int c = idx >> 5, i = idx & 31;
+      double v = (i == c) ? 1.0 : 0.0;
+      if (i < nb && c < nb && i >= c) v = S[(size_t)(k0 + c) * ld + k0 + i];
+      D[i * CS_LDD + c] = v;
+    }
+  };
+  load_diag(0, Dbuf, tid, CS_THREADS);
+  __syncthreads();
+  if (warp == 0) {
+    const int bad = cs_potf2_warp(Dbuf, invbuf, lane);
+    if (bad && lane == 0) { atomicCAS(info, 0, bad); *s_bad = 1; }
+  }
+  __syncthreads();
+  CSTICK(0);
+
+  int cur = 0;
+  for (int k0 = 0; k0 < n; k0 += CS_B, cur ^= 1) {
+    if (*s_bad) return;                            // (uniform: written before the last barrier)
+    const double* D = Dbuf + cur * CS_B * CS_LDD;
+    const double* invd = invbuf + cur * CS_B;
+    const int nb = min(CS_B, n - k0);
+    const int r0 = k0 + nb;                        // first row / column of the trailing matrix
+    const int mc = n - r0;                         // its order; row mc of the panel (global row n) is the right-hand side
+    const int m = mc + 1;
+
+    // ---- panel solve: X = A L^-T, one thread per row (right-looking over the 32 columns), L written back ----
+    if (tid < m) {
+      const int r = r0 + tid;
+      double x[CS_B];
+#pragma unroll
+      for (int c = 0; c < CS_B; ++c) x[c] = c < nb ? S[(size_t)(k0 + c) * ld + r] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CS_B; ++c) {
+        x[c] *= invd[c];
+#pragma unroll
+        for (int c2 = c + 1; c2 < CS_B; ++c2) x[c2] = fma(-x[c], D[c2 * CS_LDD + c], x[c2]);
+      }
+#pragma unroll
+      for (int c = 0; c < CS_B; ++c) {
+        if (c < nb) S[(size_t)(k0 + c) * ld + r] = x[c];
+        Xt[c * CS_LDX + tid] = x[c];
+      }
+    }
+    if (tid == 0) *s_next = 1;
+    // the factored diagonal block goes back too (lower part)
+    for (int idx = tid; idx < CS_B * CS_B; idx += CS_THREADS) {
+      const int c = idx >> 5, i = idx & 31;
+      if (i < nb && c <= i) S[(size_t)(k0 + c) * ld + k0 + i] = D[i * CS_LDD + c];
+    }
+    __syncthreads();
+    CSTICK(1);
+    if (mc == 0) break;
+
+    // ---- trailing update A -= X X^T (lower part) + the right-hand-side row ----
+    auto update_tile = [&](int ti, int tj, double* Dnext) {
+      // 32 x 32 warp tile = 4 x 4 DMMA blocks; C fragment: row g, columns 2q, 2q + 1 of each 8 x 8 block
+      const int i0 = ti * 32, j0 = tj * 32;
+      double acc[4][4][2];
+#pragma unroll
+      for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+        for (int bj = 0; bj < 4; ++bj)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = i0 + 8 * bi + g, j = j0 + 8 * bj + 2 * q + e;
+            acc[bi][bj][e] = (i < mc && j <= i) ? S[(size_t)(r0 + j) * ld + r0 + i] : 0.0;
+          }
+#pragma unroll
+      for (int kk = 0; kk < CS_B; kk += 4) {
+        double a[4], b[4];
+        const double* xr = Xt + (kk + q) * CS_LDX;
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi) a[bi] = -xr[i0 + 8 * bi + g];
+#pragma unroll
+        for (int bj = 0; bj < 4; ++bj) b[bj] = xr[j0 + 8 * bj + g];
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+          for (int bj = 0; bj < 4; ++bj) dmma(acc[bi][bj][0], acc[bi][bj][1], a[bi], b[bj]);
+      }
+#pragma unroll
+      for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+        for (int bj = 0; bj < 4; ++bj)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = i0 + 8 * bi + g, j = j0 + 8 * bj + 2 * q + e;
+            if (Dnext) {      // tile (0, 0) = the next diagonal block: straight into shared memory, identity-padded
+              Dnext[i * CS_LDD + j] = (i < mc && j <= i) ? acc[bi][bj][e] : (i == j ? 1.0 : 0.0);
+            } else if (i < mc && j <= i) {
+              S[(size_t)(r0 + j) * ld + r0 + i] = acc[bi][bj][e];
+            }
+          }
+    };
+    const int nt = (mc + 31) >> 5;
+    const int n_tiles = nt * (nt + 1) / 2;
+    const int nb_next = min(CS_B, n - r0);
+    double* Dn = Dbuf + (cur ^ 1) * CS_B * CS_LDD;
+    double* invn = invbuf + (cur ^ 1) * CS_B;
+    // the right-hand-side row: one thread per column
+    for (int j = tid; j < mc; j += CS_THREADS) {
+      double y = S[(size_t)(r0 + j) * ld + n];
+#pragma unroll
+      for (int kk = 0; kk < CS_B; ++kk) y = fma(-Xt[kk * CS_LDX + mc], Xt[kk * CS_LDX + j], y);
+      S[(size_t)(r0 + j) * ld + n] = y;
+    }
+    if (warp == 0) {
+      // look-ahead: tile (0, 0) holds the next diagonal block — update it, factorise it, then join the others
+      CSTICK(2);
+      update_tile(0, 0, Dn);
+      __syncwarp();
+      CSTICK(4);
+      const int bad = cs_potf2_warp(Dn, invn, lane);
+      CSTICK(5);
+      if (bad && lane == 0 && bad <= nb_next) { atomicCAS(info, 0, r0 + bad); *s_bad = 1; }
+    }
+    // tiles 1 .. n_tiles - 1 (tile t of row ti: index ti (ti + 1) / 2 + tj) from a shared ticket; warp 0 joins late
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(s_next, 1);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= n_tiles) break;
+      int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      while (ti * (ti + 1) / 2 > t) --ti;
+      update_tile(ti, t - ti * (ti + 1) / 2, nullptr);
+    }
+    CSTICK(6);
+    __syncthreads();
+    CSTICK(7);
+  }
+
+  // ---- backward substitution L^T x = y (y = row n of S), by 32-blocks from the end ----
+  double* Lb = Dbuf;
+  for (int j0 = ((n - 1) / CS_B) * CS_B; j0 >= 0; j0 -= CS_B) {
+    const int nb = min(CS_B, n - j0);
+    // y_j -= sum_{i >= j0 + nb} L[i][j] x_i: one warp per column, coalesced down the column
+    for (int j = warp; j < nb; j += CS_THREADS / 32) {
+      const double* col = S + (size_t)(j0 + j) * ld;
+      double s = 0.0;
+      for (int i = j0 + nb + lane; i < n; i += 32) s = fma(col[i], xs[i], s);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) invbuf[j] = col[n] - s;
+    }
+    for (int idx = tid; idx < CS_B * CS_B; idx += CS_THREADS) {
+      const int c = idx >> 5, i = idx & 31;
+      Lb[i * CS_LDD + c] = (i < nb && c <= i) ? S[(size_t)(j0 + c) * ld + j0 + i] : (i == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    CSTICK(8);
+    if (warp == 0) {
+      // lane j owns column j of the block: x_i known -> y_j -= L[i][j] x_i for j < i
+      double y = lane < nb ? invbuf[lane] : 0.0;
+      const double dinv = 1.0 / Lb[lane * CS_LDD + lane];
+      double xv = 0.0;
+#pragma unroll 4
+      for (int i = CS_B - 1; i >= 0; --i) {
+        const double l = Lb[i * CS_LDD + lane];
+        const double xi = __shfl_sync(0xffffffffu, y * dinv, i);      // lane i's y is final at step i
+        if (lane == i) xv = xi;
+        if (lane < i) y = fma(-l, xi, y);
+      }
+      if (lane < nb) xs[j0 + lane] = xv;
+    }
+    __syncthreads();
+    CSTICK(9);
+  }
+  for (int c = tid; c < n; c += CS_THREADS) rhs[c] = xs[c];
+}
+
+}  // namespace
+}  // namespace stba

@@ -245,7 +245,11 @@ struct DeviceCtx {
 };
 static DeviceCtx g_dev[64];
 
+static std::mutex g_dev_mu;
+
 static int process_init(int device) {
+  if (device < 0 || device >= 64) return STBA_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(g_dev_mu);   // engines may be created from several host threads
   DeviceCtx& d = g_dev[device];
   if (d.ready) return STBA_OK;
   cudaDeviceProp prop;
@@ -721,6 +725,8 @@ int Engine::dense_solve(int backend) {
   CK(cudaMemsetAsync(dev_info, 0, sizeof(int), stream));
   if (n > 0) {
     if (backend == STBA_DENSE_CUSOLVER || backend == STBA_DENSE_HYBRID) {
+      // the handle is shared by all engines of the device and carries the stream: enqueue under the lock
+      std::lock_guard<std::mutex> lk(g_dev_mu);
       if (!cusolver) {   // one handle per process and device, created on first use
         DeviceCtx& d = g_dev[device];
         if (!d.cusolver && cusolverDnCreate(&d.cusolver) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
@@ -1335,10 +1341,33 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return STBA_ERR_NO_DEVICE; }
   CK(cudaSetDevice(device));
   if (n == 0) { if (info) *info = 0; return STBA_OK; }
-  double *dS = nullptr, *dS0 = nullptr, *dr = nullptr, *dr0 = nullptr, *work = nullptr;
-  int* dinfo = nullptr;
-  cudaStream_t st;
-  cudaEvent_t a, b;
+  // everything this call owns; released on every return path (the CK / CKS macros return early)
+  struct Scratch {
+    double *dS = nullptr, *dS0 = nullptr, *dr = nullptr, *dr0 = nullptr, *work = nullptr;
+    int* dinfo = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    cusolverDnHandle_t h = nullptr;
+    stba::CholWorkspace ws;
+    stba::SolveWorkspace tw;
+    ~Scratch() {
+      tw.reset();
+      ws.reset();      // stream-ordered buffers: released while the stream exists
+      if (st) cudaStreamSynchronize(st);
+      if (h) cusolverDnDestroy(h);
+      cudaFree(dS); cudaFree(dS0); cudaFree(dr); cudaFree(dr0); cudaFree(dinfo); cudaFree(work);
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+      if (st) cudaStreamDestroy(st);
+    }
+  } sc;
+  double *&dS = sc.dS, *&dS0 = sc.dS0, *&dr = sc.dr, *&dr0 = sc.dr0, *&work = sc.work;
+  int*& dinfo = sc.dinfo;
+  cudaStream_t& st = sc.st;
+  cudaEvent_t &a = sc.a, &b = sc.b;
+  cusolverDnHandle_t& h = sc.h;
+  stba::CholWorkspace& ws = sc.ws;
+  stba::SolveWorkspace& tw = sc.tw;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
   const int ld = n + 2;
@@ -1349,10 +1378,7 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
   CK(cudaMemcpy2D(dS0, (size_t)ld * sizeof(double), S, (size_t)n * sizeof(double), (size_t)n * sizeof(double), n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dr0, rhs, n * sizeof(double), cudaMemcpyHostToDevice));
   int rc = STBA_OK;
-  cusolverDnHandle_t h = nullptr;
   int lwork = 0;
-  stba::CholWorkspace ws;
-  stba::SolveWorkspace tw;
   const bool lib_factor = backend == STBA_DENSE_CUSOLVER || backend == STBA_DENSE_HYBRID;
   if (lib_factor) {
     if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return STBA_ERR_SOLVER;
@@ -1385,12 +1411,6 @@ int stba_dense_cholesky_solve(int device, int backend, int n, const double* S, c
     CK(cudaMemcpy(x, dr, n * sizeof(double), cudaMemcpyDeviceToHost));
     if (info) CK(cudaMemcpy(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost));
   }
-  tw.reset();
-  ws.reset();      // stream-ordered buffers: released while the stream exists
-  cudaStreamSynchronize(st);
-  if (h) cusolverDnDestroy(h);
-  cudaFree(dS); cudaFree(dS0); cudaFree(dr); cudaFree(dr0); cudaFree(dinfo); if (work) cudaFree(work);
-  cudaEventDestroy(a); cudaEventDestroy(b); cudaStreamDestroy(st);
   return rc;
 }
 

@@ -325,7 +325,7 @@ def test_config_C_full_solve_against_golden(stba, scene_C):
 
 
 # ---- the dense reduced-camera solve in isolation -----------------------------------------------
-@pytest.mark.parametrize("n", [6, 30, 126, 128, 132, 258, 1002, 2994])
+@pytest.mark.parametrize("n", [6, 30, 126, 128, 132, 258, 288, 320, 322, 1002, 2994])
 @pytest.mark.parametrize("backend", ["own", "cusolver", "hybrid"])
 def test_dense_cholesky_solve(stba, n, backend):
     rng = np.random.default_rng(n)
