@@ -21,36 +21,37 @@ constexpr int CS_MAXN = 512;                   // largest n served (rows below a
 constexpr int CS_DEFAULT_N = 320;               // systems up to this order take this path (measured: 0.166 ms against 0.205 ms at n = 288, 0.267 against 0.216 at n = 384; STBA_CHOL_SMALL_N overrides)
 constexpr int CS_LDX = CS_MAXN + 4;            // k-major panel: (q * CS_LDX + g) mod 16 distinct for q, g < 4 (8-byte banks)
 constexpr int CS_LDD = CS_B + 1;               // diagonal block, row-major, padded
-constexpr int CS_SMEM = (CS_B * CS_LDX + 2 * CS_B * CS_LDD + 2 * CS_B + CS_MAXN + 8) * (int)sizeof(double);
+constexpr int CS_SMEM = (CS_B * CS_LDX + 2 * CS_B * CS_LDD + 2 * CS_B + CS_MAXN + 64 + 16) * (int)sizeof(double);
 
 // Cholesky of the 32 x 32 block in D (row-major, ld CS_LDD, lower part valid, identity-padded), by ONE warp, lane =
-// row, left-looking: column j = (a_ij - sum_{c<j} l_ic l_jc) / l_jj with the own row in registers and row j read from
-// shared memory (broadcast).  invd[j] = 1 / l_jj.  Returns the 1-based index of the first non-positive pivot or 0.
-__device__ __noinline__ int cs_potf2_warp(double* D, double* invd, int lane) {
-  // (own row in registers, fully unrolled: a rolled variant with the row in shared memory measured 2 x slower —
-  // every term of the dependent chain then waits for two shared-memory loads)
+// row, the row in registers, right-looking: at step j every lane publishes its column-j entry in shared memory, one
+// __syncwarp later all lanes read the column back as broadcasts (the pivot loop of potrf128_dev, stba_chol.cu: shuffles
+// inside a warp-specialised branch compile to WARPSYNC.COLLECTIVE call sequences, several times slower).
+// invd[j] = 1 / l_jj.  `cb` = 64 doubles of scratch.  Returns the 1-based index of the first non-positive pivot or 0.
+__device__ __forceinline__ int cs_potf2_warp(double* D, double* invd, double* cb, int lane) {
   double a[CS_B];
 #pragma unroll
-  for (int c = 0; c < CS_B; ++c) a[c] = D[lane * CS_LDD + c];
+  for (int c = 0; c < CS_B; ++c) a[c] = (c <= lane) ? D[lane * CS_LDD + c] : 0.0;
   int bad = 0;
 #pragma unroll
   for (int j = 0; j < CS_B; ++j) {
-    double v0 = a[j], v1 = 0.0;
-#pragma unroll
-    for (int c = 0; c < j; ++c) {
-      const double l = D[j * CS_LDD + c];
-      if (c & 1) v1 = fma(-a[c], l, v1);
-      else v0 = fma(-a[c], l, v0);
-    }
-    const double v = v0 + v1;
-    const double d = __shfl_sync(0xffffffffu, v, j);
-    if (!(d > 0.0) && !bad) bad = j + 1;
-    const double rs = fast_rsqrt(d);
-    a[j] = lane == j ? d * rs : (lane > j ? v * rs : 0.0);
-    if (lane >= j) D[lane * CS_LDD + j] = a[j];
-    if (lane == j) invd[j] = rs;
+    double* col = cb + (j & 1) * 32;
+    col[lane] = a[j];
     __syncwarp();
+    const double d = col[j];
+    if (!(d > 0.0) && !bad) bad = j + 1;
+    const double inv = fast_rsqrt(d);
+    const double lj = a[j] * inv;
+    const double t = lj * inv;
+#pragma unroll
+    for (int k = j + 1; k < CS_B; ++k) a[k] = fma(-t, col[k], a[k]);      // lanes < k: unused upper values
+    a[j] = (lane == j) ? d * inv : lj;
+    if (lane == j) invd[j] = inv;
   }
+#pragma unroll
+  for (int c = 0; c < CS_B; ++c)
+    if (c <= lane) D[lane * CS_LDD + c] = a[c];
+  __syncwarp();
   return bad;
 }
 
@@ -68,8 +69,10 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
   double* Dbuf = Xt + CS_B * CS_LDX;               // two diagonal blocks (current, next)
   double* invbuf = Dbuf + 2 * CS_B * CS_LDD;       // their inverse diagonals
   double* xs = invbuf + 2 * CS_B;                  // backward substitution: solution so far
-  int* s_bad = reinterpret_cast<int*>(xs + CS_MAXN);
-  int* s_next = s_bad + 1;                         // ticket of the trailing-update tiles
+  double* cbuf = xs + CS_MAXN;                     // 64: column exchange of the pivot loop / of the backward solve
+  int* s_bad = reinterpret_cast<int*>(cbuf + 64);
+  int* s_next = s_bad + 1;
+  int* s_tk = s_bad + 2;                           // per-warp ticket broadcast (16)                         // ticket of the trailing-update tiles
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;           // DMMA fragment coordinates
 
@@ -92,7 +95,7 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
   load_diag(0, Dbuf, tid, CS_THREADS);
   __syncthreads();
   if (warp == 0) {
-    const int bad = cs_potf2_warp(Dbuf, invbuf, lane);
+    const int bad = cs_potf2_warp(Dbuf, invbuf, cbuf, lane);
     if (bad && lane == 0) { atomicCAS(info, 0, bad); *s_bad = 1; }
   }
   __syncthreads();
@@ -182,8 +185,8 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
     const int nb_next = min(CS_B, n - r0);
     double* Dn = Dbuf + (cur ^ 1) * CS_B * CS_LDD;
     double* invn = invbuf + (cur ^ 1) * CS_B;
-    // the right-hand-side row: one thread per column
-    for (int j = tid; j < mc; j += CS_THREADS) {
+    // the right-hand-side row: one thread per column (warps 1 .. 15: warp 0 is on the critical path)
+    for (int j = warp ? tid - 32 : mc; j < mc; j += CS_THREADS - 32) {
       double y = S[(size_t)(r0 + j) * ld + n];
 #pragma unroll
       for (int kk = 0; kk < CS_B; ++kk) y = fma(-Xt[kk * CS_LDX + mc], Xt[kk * CS_LDX + j], y);
@@ -195,15 +198,16 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
       update_tile(0, 0, Dn);
       __syncwarp();
       CSTICK(4);
-      const int bad = cs_potf2_warp(Dn, invn, lane);
+      const int bad = cs_potf2_warp(Dn, invn, cbuf, lane);
       CSTICK(5);
       if (bad && lane == 0 && bad <= nb_next) { atomicCAS(info, 0, r0 + bad); *s_bad = 1; }
     }
     // tiles 1 .. n_tiles - 1 (tile t of row ti: index ti (ti + 1) / 2 + tj) from a shared ticket; warp 0 joins late
     for (;;) {
-      int t = 0;
-      if (lane == 0) t = atomicAdd(s_next, 1);
-      t = __shfl_sync(0xffffffffu, t, 0);
+      if (lane == 0) s_tk[warp] = atomicAdd(s_next, 1);
+      __syncwarp();
+      const int t = s_tk[warp];
+      __syncwarp();
       if (t >= n_tiles) break;
       int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
       while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
@@ -242,8 +246,10 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
 #pragma unroll 4
       for (int i = CS_B - 1; i >= 0; --i) {
         const double l = Lb[i * CS_LDD + lane];
-        const double xi = __shfl_sync(0xffffffffu, y * dinv, i);      // lane i's y is final at step i
-        if (lane == i) xv = xi;
+        double* slot = cbuf + (i & 1) * 32;
+        if (lane == i) { xv = y * dinv; *slot = xv; }      // lane i's y is final at step i
+        __syncwarp();
+        const double xi = *slot;
         if (lane < i) y = fma(-l, xi, y);
       }
       if (lane < nb) xs[j0 + lane] = xv;
