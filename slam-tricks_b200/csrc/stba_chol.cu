@@ -3048,16 +3048,16 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
     if (n <= small_n) {
       static std::once_flag once;
       static cudaError_t attr_rc = cudaSuccess;
-      std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM); });
+      std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM + CS_SMEM_CLK); });
       CKC(attr_rc);
-      k_chol_small<<<1, CS_THREADS, CS_SMEM, stream>>>(S, ld, n, rhs, dev_info);
+      k_chol_small<<<1, CS_THREADS, CS_SMEM + CS_SMEM_CLK, stream>>>(S, ld, n, rhs, dev_info);
       CKC(cudaGetLastError());
 #ifdef STBA_CS_TIMING
       {
         cudaStreamSynchronize(stream);
         long long h[16];
         cudaMemcpyFromSymbol(h, g_cs_clk, sizeof(h));
-        fprintf(stderr, "[chol small n=%d] cycles: init+potf2 %lld | panel solve %lld | rhs row %lld tile00 %lld load %lld potf2 %lld tiles %lld barrier %lld | bwd gemv %lld bwd solve %lld\n",
+        fprintf(stderr, "[chol small n=%d] cycles of warp 0: init+potf2 %lld | panel solve+barrier %lld | (unused %lld %lld) tile00 %lld potf2 %lld tiles %lld barrier %lld | bwd products+barrier %lld bwd solve+barrier %lld\n",
                 n, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
       }
 #endif

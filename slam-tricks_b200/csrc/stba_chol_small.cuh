@@ -56,10 +56,13 @@ __device__ __forceinline__ int cs_potf2_warp(double* D, double* invd, double* cb
 }
 
 #ifdef STBA_CS_TIMING
+// phase clocks of warp 0 (every lane ticks, so that the warp stays converged; lane 0's sums are reported)
 __device__ long long g_cs_clk[16];
-#define CSTICK(slot) do { if (tid == 0) { const long long now_ = clock64(); g_cs_clk[slot] += now_ - t_last; t_last = now_; } } while (0)
+#define CSTICK(slot) do { if (warp == 0) { const long long now_ = clock64(); s_clk[(slot) * 32 + lane] += now_ - t_last; t_last = now_; } } while (0)
+constexpr int CS_SMEM_CLK = 16 * 32 * 8;
 #else
 #define CSTICK(slot) do {} while (0)
+constexpr int CS_SMEM_CLK = 0;
 #endif
 
 __global__ void __launch_bounds__(CS_THREADS, 1)
@@ -77,8 +80,9 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
   const int g = lane >> 2, q = lane & 3;           // DMMA fragment coordinates
 
 #ifdef STBA_CS_TIMING
+  long long* s_clk = reinterpret_cast<long long*>(cs_sm) + CS_SMEM / 8;
+  if (warp == 0) for (int k = 0; k < 16; ++k) s_clk[k * 32 + lane] = 0;
   long long t_last = clock64();
-  if (tid == 0) for (int k = 0; k < 16; ++k) g_cs_clk[k] = 0;
 #endif
   if (tid == 0) *s_bad = 0;
   for (int c = tid; c < n; c += CS_THREADS) S[(size_t)c * ld + n] = rhs[c];      // the augmented row
@@ -258,6 +262,9 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
     CSTICK(9);
   }
   for (int c = tid; c < n; c += CS_THREADS) rhs[c] = xs[c];
+#ifdef STBA_CS_TIMING
+  if (tid < 16) g_cs_clk[tid] = s_clk[tid * 32];
+#endif
 }
 
 }  // namespace
