@@ -3057,8 +3057,8 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
         cudaStreamSynchronize(stream);
         long long h[16];
         cudaMemcpyFromSymbol(h, g_cs_clk, sizeof(h));
-        fprintf(stderr, "[chol small n=%d] cycles of warp 0: init+potf2 %lld | panel solve+barrier %lld | (unused %lld %lld) tile00 %lld potf2 %lld tiles %lld barrier %lld | bwd products+barrier %lld bwd solve+barrier %lld\n",
-                n, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+        fprintf(stderr, "[chol small n=%d] cycles of warp 0: init+potf2 %lld | panel solve+barrier %lld | (unused %lld %lld) tile00 %lld potf2 %lld tiles %lld barrier %lld | bwd products+barrier %lld bwd solve+barrier %lld | panel solve: loads %lld chain %lld stores %lld\n",
+                n, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12]);
       }
 #endif
       if (n_launches) *n_launches += 1;

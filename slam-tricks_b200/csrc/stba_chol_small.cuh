@@ -21,38 +21,56 @@ constexpr int CS_MAXN = 512;                   // largest n served (rows below a
 constexpr int CS_DEFAULT_N = 320;               // systems up to this order take this path (measured: 0.166 ms against 0.205 ms at n = 288, 0.267 against 0.216 at n = 384; STBA_CHOL_SMALL_N overrides)
 constexpr int CS_LDX = CS_MAXN + 4;            // k-major panel: (q * CS_LDX + g) mod 16 distinct for q, g < 4 (8-byte banks)
 constexpr int CS_LDD = CS_B + 1;               // diagonal block, row-major, padded
-constexpr int CS_SMEM = (CS_B * CS_LDX + 2 * CS_B * CS_LDD + 2 * CS_B + CS_MAXN + 64 + 16) * (int)sizeof(double);
+constexpr int CS_LDT = CS_B + 2;               // its factor, column-major, rows 16-byte aligned
+constexpr int CS_SMEM = (CS_B * CS_LDX + 2 * CS_B * CS_LDD + 2 * CS_B + CS_MAXN + 1024 + CS_B * CS_LDT + 16) * (int)sizeof(double);      // (the tail: 20 ints)
 
-// Cholesky of the 32 x 32 block in D (row-major, ld CS_LDD, lower part valid, identity-padded), by ONE warp, lane =
-// row, the row in registers, right-looking: at step j every lane publishes its column-j entry in shared memory, one
-// __syncwarp later all lanes read the column back as broadcasts (the pivot loop of potrf128_dev, stba_chol.cu: shuffles
-// inside a warp-specialised branch compile to WARPSYNC.COLLECTIVE call sequences, several times slower).
-// invd[j] = 1 / l_jj.  `cb` = 64 doubles of scratch.  Returns the 1-based index of the first non-positive pivot or 0.
-__device__ __forceinline__ int cs_potf2_warp(double* D, double* invd, double* cb, int lane) {
+// Cholesky of the 32 x 32 block in D (row-major, ld CS_LDD, lower part valid, identity-padded) by ONE warp, lane = row,
+// the row in registers: the pivot chain of potrf128_prog_dev (stba_chol.cu) — elimination on UNSCALED values, column
+// j + 1 exchanged through shared memory one dependent operation after the reciprocal of pivot j, the rest of the
+// rank-1 update of step j issued inside step j + 1 where it fills the latency of the exchange and of the reciprocal;
+// the columns are scaled by 1 / sqrt(d_j) once at the end.  No shuffles (inside a warp-specialised branch they compile
+// to WARPSYNC.COLLECTIVE call sequences).  Output: Lt[c * CS_LDT + r] = L(r, c) (column-major: the panel solve reads a
+// column of L with 16-byte broadcasts), invd[j] = 1 / L(j, j).  cb = 32 x 32 doubles of scratch.
+// Returns the 1-based index of the first non-positive pivot or 0.
+__device__ __forceinline__ int cs_potf2_warp(const double* D, double* Lt, double* invd, double* cb, int lane) {
   double a[CS_B];
 #pragma unroll
   for (int c = 0; c < CS_B; ++c) a[c] = (c <= lane) ? D[lane * CS_LDD + c] : 0.0;
-  int bad = 0;
+  cb[lane] = a[0];
+  __syncwarp();
+  double tp = 0.0;
 #pragma unroll
   for (int j = 0; j < CS_B; ++j) {
-    double* col = cb + (j & 1) * 32;
-    col[lane] = a[j];
-    __syncwarp();
+    const double* col = cb + j * 32;
     const double d = col[j];
-    if (!(d > 0.0) && !bad) bad = j + 1;
-    const double inv = fast_rsqrt(d);
-    const double lj = a[j] * inv;
-    const double t = lj * inv;
+    const double nx = (j + 1 < CS_B) ? col[j + 1] : 0.0;
+    if (j > 0) {
+      const double* pc = cb + (j - 1) * 32;
 #pragma unroll
-    for (int k = j + 1; k < CS_B; ++k) a[k] = fma(-t, col[k], a[k]);      // lanes < k: unused upper values
-    a[j] = (lane == j) ? d * inv : lj;
-    if (lane == j) invd[j] = inv;
+      for (int k = j + 2; k < CS_B; ++k) a[k] = fma(-tp, pc[k], a[k]);
+    }
+    const double u = a[j] * nx;
+    const double r = fast_rcp(d);
+    if (j + 1 < CS_B) {
+      a[j + 1] = fma(-u, r, a[j + 1]);
+      cb[(j + 1) * 32 + lane] = a[j + 1];
+      __syncwarp();
+    }
+    tp = a[j] * r;
+    if (j + 2 < CS_B) a[j + 2] = fma(-tp, col[j + 2], a[j + 2]);
   }
-#pragma unroll
-  for (int c = 0; c < CS_B; ++c)
-    if (c <= lane) D[lane * CS_LDD + c] = a[c];
+  const double dl = cb[lane * 32 + lane];
+  const unsigned badm = __ballot_sync(0xffffffffu, !(dl > 0.0));
+  const double rsl = fast_rsqrt(dl);
+  invd[lane] = rsl;
   __syncwarp();
-  return bad;
+#pragma unroll
+  for (int c = 0; c < CS_B; ++c) {
+    const double v = (c == lane) ? dl * rsl : a[c] * invd[c];
+    if (c <= lane) Lt[c * CS_LDT + lane] = v;
+  }
+  __syncwarp();
+  return badm ? __ffs(badm) : 0;
 }
 
 #ifdef STBA_CS_TIMING
@@ -72,10 +90,11 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
   double* Dbuf = Xt + CS_B * CS_LDX;               // two diagonal blocks (current, next)
   double* invbuf = Dbuf + 2 * CS_B * CS_LDD;       // their inverse diagonals
   double* xs = invbuf + 2 * CS_B;                  // backward substitution: solution so far
-  double* cbuf = xs + CS_MAXN;                     // 64: column exchange of the pivot loop / of the backward solve
-  int* s_bad = reinterpret_cast<int*>(cbuf + 64);
+  double* cbuf = xs + CS_MAXN;                     // 32 x 32: column exchange of the pivot loop / of the backward solve
+  double* Lt = cbuf + 1024;                        // factor of the current diagonal block, column-major
+  int* s_bad = reinterpret_cast<int*>(Lt + CS_B * CS_LDT);
   int* s_next = s_bad + 1;
-  int* s_tk = s_bad + 2;                           // per-warp ticket broadcast (16)                         // ticket of the trailing-update tiles
+  int* s_tk = s_bad + 4;                           // per-warp ticket broadcast (16)                         // ticket of the trailing-update tiles
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;           // DMMA fragment coordinates
 
@@ -99,7 +118,7 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
   load_diag(0, Dbuf, tid, CS_THREADS);
   __syncthreads();
   if (warp == 0) {
-    const int bad = cs_potf2_warp(Dbuf, invbuf, cbuf, lane);
+    const int bad = cs_potf2_warp(Dbuf, Lt, invbuf, cbuf, lane);
     if (bad && lane == 0) { atomicCAS(info, 0, bad); *s_bad = 1; }
   }
   __syncthreads();
@@ -108,7 +127,6 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
   int cur = 0;
   for (int k0 = 0; k0 < n; k0 += CS_B, cur ^= 1) {
     if (*s_bad) return;                            // (uniform: written before the last barrier)
-    const double* D = Dbuf + cur * CS_B * CS_LDD;
     const double* invd = invbuf + cur * CS_B;
     const int nb = min(CS_B, n - k0);
     const int r0 = k0 + nb;                        // first row / column of the trailing matrix
@@ -121,23 +139,29 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
       double x[CS_B];
 #pragma unroll
       for (int c = 0; c < CS_B; ++c) x[c] = c < nb ? S[(size_t)(k0 + c) * ld + r] : 0.0;
+#ifdef STBA_CS_TIMING
+      if (x[0] == 1.2345e300) x[1] = 0.0;      // (wait for the loads)
+#endif
+      CSTICK(10);
 #pragma unroll
       for (int c = 0; c < CS_B; ++c) {
         x[c] *= invd[c];
 #pragma unroll
-        for (int c2 = c + 1; c2 < CS_B; ++c2) x[c2] = fma(-x[c], D[c2 * CS_LDD + c], x[c2]);
+        for (int c2 = c + 1; c2 < CS_B; ++c2) x[c2] = fma(-x[c], Lt[c * CS_LDT + c2], x[c2]);
       }
+      CSTICK(11);
 #pragma unroll
       for (int c = 0; c < CS_B; ++c) {
         if (c < nb) S[(size_t)(k0 + c) * ld + r] = x[c];
         Xt[c * CS_LDX + tid] = x[c];
       }
+      CSTICK(12);
     }
     if (tid == 0) *s_next = 1;
     // the factored diagonal block goes back too (lower part)
     for (int idx = tid; idx < CS_B * CS_B; idx += CS_THREADS) {
       const int c = idx >> 5, i = idx & 31;
-      if (i < nb && c <= i) S[(size_t)(k0 + c) * ld + k0 + i] = D[i * CS_LDD + c];
+      if (i < nb && c <= i) S[(size_t)(k0 + c) * ld + k0 + i] = Lt[c * CS_LDT + i];
     }
     __syncthreads();
     CSTICK(1);
@@ -202,11 +226,14 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
       update_tile(0, 0, Dn);
       __syncwarp();
       CSTICK(4);
-      const int bad = cs_potf2_warp(Dn, invn, cbuf, lane);
+      const int bad = cs_potf2_warp(Dn, Lt, invn, cbuf, lane);
       CSTICK(5);
       if (bad && lane == 0 && bad <= nb_next) { atomicCAS(info, 0, r0 + bad); *s_bad = 1; }
     }
-    // tiles 1 .. n_tiles - 1 (tile t of row ti: index ti (ti + 1) / 2 + tj) from a shared ticket; warp 0 joins late
+    // tiles 1 .. n_tiles - 1 (tile t of row ti: index ti (ti + 1) / 2 + tj) from a shared ticket; warp 0 joins late.
+    // (Keeping the warps that share warp 0's scheduler out of the tile loop until the pivot chain is done halves the
+    // chain — 12 k -> 6.6 k cycles per block, their DMMAs queue in front of its dependent operations — but the tiles
+    // they do not take arrive later by as much: 0.146 -> 0.152 ms at n = 288, not kept.)
     for (;;) {
       if (lane == 0) s_tk[warp] = atomicAdd(s_next, 1);
       __syncwarp();
