@@ -250,28 +250,28 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
     CSTICK(7);
   }
 
-  // ---- backward substitution L^T x = y (y = row n of S), by 32-blocks from the end ----
-  double* Lb = Dbuf;
-  for (int j0 = ((n - 1) / CS_B) * CS_B; j0 >= 0; j0 -= CS_B) {
+  // ---- backward substitution L^T x = y (y = row n of S), right-looking by 32-blocks from the end: xs holds y until a
+  //      block is solved, then x.  Per block: one warp solves the 32 x 32 triangle, then every thread j < j0 takes the
+  //      block's 32 rows out of its y_j (its own 256 contiguous bytes of column j: all loads in flight together) while
+  //      the next diagonal block is fetched — one L2 round trip per block hop. ----
+  for (int c = tid; c < n; c += CS_THREADS) xs[c] = S[(size_t)c * ld + n];
+  auto load_lb = [&](int j0, double* Lb) {
     const int nb = min(CS_B, n - j0);
-    // y_j -= sum_{i >= j0 + nb} L[i][j] x_i: one warp per column, coalesced down the column
-    for (int j = warp; j < nb; j += CS_THREADS / 32) {
-      const double* col = S + (size_t)(j0 + j) * ld;
-      double s = 0.0;
-      for (int i = j0 + nb + lane; i < n; i += 32) s = fma(col[i], xs[i], s);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) invbuf[j] = col[n] - s;
-    }
     for (int idx = tid; idx < CS_B * CS_B; idx += CS_THREADS) {
       const int c = idx >> 5, i = idx & 31;
       Lb[i * CS_LDD + c] = (i < nb && c <= i) ? S[(size_t)(j0 + c) * ld + j0 + i] : (i == c ? 1.0 : 0.0);
     }
-    __syncthreads();
-    CSTICK(8);
+  };
+  const int j_last = ((n - 1) / CS_B) * CS_B;
+  load_lb(j_last, Dbuf);
+  __syncthreads();
+  int pb = 0;
+  for (int j0 = j_last; j0 >= 0; j0 -= CS_B, pb ^= 1) {
+    const int nb = min(CS_B, n - j0);
+    const double* Lb = Dbuf + pb * CS_B * CS_LDD;
     if (warp == 0) {
       // lane j owns column j of the block: x_i known -> y_j -= L[i][j] x_i for j < i
-      double y = lane < nb ? invbuf[lane] : 0.0;
+      double y = lane < nb ? xs[j0 + lane] : 0.0;
       const double dinv = 1.0 / Lb[lane * CS_LDD + lane];
       double xv = 0.0;
 #pragma unroll 4
@@ -285,6 +285,26 @@ k_chol_small(double* __restrict__ S, int ld, int n, double* __restrict__ rhs, in
       }
       if (lane < nb) xs[j0 + lane] = xv;
     }
+    __syncthreads();
+    CSTICK(8);
+    if (j0 == 0) break;
+    for (int j = tid; j < j0; j += CS_THREADS) {
+      const double* col = S + (size_t)j * ld + j0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      if (nb == CS_B) {
+#pragma unroll
+        for (int i = 0; i < CS_B; i += 4) {
+          s0 = fma(col[i], xs[j0 + i], s0);
+          s1 = fma(col[i + 1], xs[j0 + i + 1], s1);
+          s2 = fma(col[i + 2], xs[j0 + i + 2], s2);
+          s3 = fma(col[i + 3], xs[j0 + i + 3], s3);
+        }
+      } else {
+        for (int i = 0; i < nb; ++i) s0 = fma(col[i], xs[j0 + i], s0);
+      }
+      xs[j] -= (s0 + s1) + (s2 + s3);
+    }
+    load_lb(j0 - CS_B, Dbuf + (pb ^ 1) * CS_B * CS_LDD);
     __syncthreads();
     CSTICK(9);
   }
