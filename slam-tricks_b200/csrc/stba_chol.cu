@@ -3046,10 +3046,18 @@ int chol_factor_solve(CholWorkspace& ws, double* S, int n, int ld, double* rhs, 
     // small systems: one launch of one CTA (stba_chol_small.cuh); STBA_CHOL_SMALL_N=0 sends everything to the DAG kernel
     static const int small_n = std::min(CS_MAXN, getenv("STBA_CHOL_SMALL_N") ? atoi(getenv("STBA_CHOL_SMALL_N")) : CS_DEFAULT_N);
     if (n <= small_n) {
-      static std::once_flag once;
-      static cudaError_t attr_rc = cudaSuccess;
-      std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM + CS_SMEM_CLK); });
-      CKC(attr_rc);
+      {
+        // the shared-memory opt-in is a per-device attribute
+        static std::mutex mu;
+        static bool done[64] = {};
+        int dev = 0;
+        CKC(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || !done[dev]) {
+          CKC(cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM + CS_SMEM_CLK));
+          if (dev >= 0 && dev < 64) done[dev] = true;
+        }
+      }
       k_chol_small<<<1, CS_THREADS, CS_SMEM + CS_SMEM_CLK, stream>>>(S, ld, n, rhs, dev_info);
       CKC(cudaGetLastError());
 #ifdef STBA_CS_TIMING
