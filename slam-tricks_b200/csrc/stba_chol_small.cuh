@@ -1,5 +1,5 @@
-// Dense reduced-camera solve for SMALL systems (n <= 512: BASELINE configs[1], 50 cameras -> n = 288; PnP-sized and
-// calibration-sized Schur complements): ONE launch, ONE CTA.
+// Dense reduced-camera solve for SMALL systems (n <= 320 by default, 512 at most: BASELINE configs[1], 50 cameras ->
+// n = 288): ONE launch, ONE CTA.
 //
 // The 128-block DAG kernel (k_chol_dag2) needs three panel steps at n = 288 and each of them is a chain of one-CTA
 // tasks (diagonal block 128 x 128, panel solve, tile update) with a flag round trip in between: 0.21 ms, of which the
@@ -7,7 +7,7 @@
 // SM: 32-column panels, the factored panel X kept in shared memory (k-major, so that the DMMA fragments of the
 // trailing update are conflict-free 8-byte loads), the trailing matrix updated in place in L2 by 32 x 32 warp tiles
 // on the FP64 tensor pipe (mma.sync.m8n8k4.f64), the right-hand side riding along as row n of S (forward substitution
-// for free), the backward substitution by 32-blocks at the end.  Look-ahead: warp 0 factorises the next diagonal block
+// for free), the backward substitution right-looking by 32-blocks at the end.  Look-ahead: warp 0 factorises the next diagonal block
 // while the other warps are still updating the rest of the trailing matrix.
 // Fixed summation orders, no atomics on data: bit-reproducible.  Same contract as chol_factor_solve (stba_chol.cuh).
 #pragma once
@@ -18,7 +18,7 @@ namespace {
 constexpr int CS_B = 32;                       // panel width
 constexpr int CS_THREADS = 512;
 constexpr int CS_MAXN = 512;                   // largest n served (rows below a panel: n + 1 - 32 <= 481 threads)
-constexpr int CS_DEFAULT_N = 320;               // systems up to this order take this path (measured: 0.166 ms against 0.205 ms at n = 288, 0.267 against 0.216 at n = 384; STBA_CHOL_SMALL_N overrides)
+constexpr int CS_DEFAULT_N = 320;               // systems up to this order take this path (measured: 0.144 ms against 0.205 ms at n = 288, 0.247 against 0.216 at n = 384; STBA_CHOL_SMALL_N overrides)
 constexpr int CS_LDX = CS_MAXN + 4;            // k-major panel: (q * CS_LDX + g) mod 16 distinct for q, g < 4 (8-byte banks)
 constexpr int CS_LDD = CS_B + 1;               // diagonal block, row-major, padded
 constexpr int CS_LDT = CS_B + 2;               // its factor, column-major, rows 16-byte aligned
